@@ -1,0 +1,95 @@
+/* zkm_b200 — C ABI of the B200-native STARK proving path for zkMIPS/zkm.
+ *
+ * The reference has no FFI for this path (it is a plain Rust call chain); this header is what a
+ * `#[cfg(feature = "b200")]` shim inside reference prover/src/prover.rs would bind (INTEGRATION.md
+ * shows the Rust `extern "C"` block).  Conventions follow the only FFI that exists in the reference
+ * tree, the Groth16 wrapper (recursion/src/snark/snarks.rs:7-20,49-57): every entry point returns an
+ * int status (0 = ok, -1 = error) and, on error, stores a malloc'ed NUL-terminated message in *err
+ * which the caller releases with zkm_b200_free_string().
+ *
+ * Field elements are Goldilocks (p = 2^64 - 2^32 + 1) canonical u64, little endian — the memory image
+ * of plonky2's `GoldilocksField(u64)` after `to_canonical_u64()`.  Extension elements are 2 u64.
+ * Digests ("HashOut") are 4 u64.
+ *
+ * Threading: one context per process and device; calls are not re-entrant.
+ */
+#ifndef ZKM_B200_H
+#define ZKM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One STARK table's trace: `PolynomialValues<F>` per column (reference prover.rs:133,
+ * trace_poly_values: [Vec<PolynomialValues<F>>; NUM_TABLES]).  cols[c] points at 2^log_n u64. */
+typedef struct {
+    const uint64_t* const* cols;
+    uint32_t ncols;
+    uint32_t log_n;
+} zkm_table_t;
+
+/* StarkConfig / FriConfig (reference prover/src/config.rs:4-29). */
+typedef struct {
+    uint32_t rate_bits;        /* 2  */
+    uint32_t cap_height;       /* 4  */
+    uint32_t pow_bits;         /* 16 */
+    uint32_t num_queries;      /* 37 */
+    uint32_t num_challenges;   /* 2  */
+    uint32_t arity_bits;       /* 4  (ConstantArityBits(4, 5)) */
+    uint32_t final_poly_bits;  /* 5  */
+} zkm_stark_config_t;
+
+/* Opaque device-resident PolynomialBatch (coefficients + LDE + Merkle tree). */
+typedef struct zkm_batch zkm_batch_t;
+
+void zkm_b200_free_string(char* s);
+void zkm_b200_free(void* p);
+
+/* StarkConfig::standard_fast_config() (config.rs:17-29). */
+void zkm_b200_standard_fast_config(zkm_stark_config_t* out);
+
+/* Create the CUDA context, streams and twiddle tables on `device`.  Fails (no CPU fallback) when no
+ * usable GPU is present. */
+int zkm_b200_init(int device, char** err);
+int zkm_b200_shutdown(char** err);
+/* Number of CUDA kernels launched by this library since init (for bench.py's gpu_launches). */
+uint64_t zkm_b200_launch_count(void);
+/* Blocks until all device work queued by the library has finished. */
+int zkm_b200_sync(char** err);
+
+/* ---- staged API (stage-by-stage parity against the oracle) ------------------------------- */
+
+/* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height) — prover.rs:154-163,
+ * 514-521.  Host columns in; cap_out receives (1<<cap_height)*4 u64. */
+int zkm_b200_commit_values(const zkm_table_t* table, uint32_t rate_bits, uint32_t cap_height,
+                           zkm_batch_t** out, uint64_t* cap_out, char** err);
+/* PolynomialBatch::from_coeffs — prover.rs:576-587. */
+int zkm_b200_commit_coeffs(const zkm_table_t* table, uint32_t rate_bits, uint32_t cap_height,
+                           zkm_batch_t** out, uint64_t* cap_out, char** err);
+/* Same as commit_values but the columns are already in device memory: `d_values` is a device pointer
+ * to ncols*2^log_n u64, column-major.  Used by bench.py for the HBM-resident `value` metric. */
+int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint32_t log_n,
+                                  uint32_t rate_bits, uint32_t cap_height, zkm_batch_t** out,
+                                  uint64_t* cap_out, char** err);
+void zkm_b200_batch_free(zkm_batch_t* b);
+/* Coefficients of polynomial `col` (2^log_n u64). */
+int zkm_b200_batch_get_coeffs(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err);
+/* LDE values of polynomial `col` on 7*H_{4n} in natural order (2^(log_n+rate_bits) u64). */
+int zkm_b200_batch_get_lde(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err);
+/* MerkleTree::get(leaf) + MerkleTree::prove(leaf): leaf_out gets ncols u64, siblings_out gets
+ * (log_n + rate_bits - cap_height)*4 u64, leaf level first. */
+int zkm_b200_batch_open(const zkm_batch_t* b, uint32_t leaf_index, uint64_t* leaf_out,
+                        uint64_t* siblings_out, char** err);
+
+/* Raw transforms on host buffers (column-major, ncols x 2^log_n), for NTT parity tests.
+ * kind: 0 = fft, 1 = ifft, 2 = coset_ifft(7). */
+int zkm_b200_ntt(uint64_t* data, uint32_t ncols, uint32_t log_n, int kind, char** err);
+/* Poseidon permutations on `count` independent 12-word states (host buffer), run on the GPU. */
+int zkm_b200_poseidon_permute(uint64_t* states, size_t count, char** err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKM_B200_H */

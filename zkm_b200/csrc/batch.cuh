@@ -1,0 +1,35 @@
+// Device-resident PolynomialBatch (coefficients + coset-major LDE + Poseidon Merkle tree) and the
+// process-wide device context.  Mirrors plonky2's fri::oracle::PolynomialBatch as used by the
+// reference (prover/src/prover.rs:154-163,514-521,576-587; fields evidenced at prover.rs:180,687).
+#pragma once
+#include "dev.cuh"
+#include "ntt.cuh"
+#include "merkle.cuh"
+
+namespace zkm {
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = 0;
+    NttTables ntt;
+};
+Ctx& ctx();                    // throws if zkm_b200_init has not succeeded
+bool ctx_ready();
+void ctx_init(int device);
+void ctx_shutdown();
+
+struct Batch {
+    int ncols = 0, log_n = 0, rate_bits = 0, cap_height = 0;
+    DevBuf coeffs;             // ncols x n            (column-major, natural order)
+    DevBuf lde;                // ncols x (n<<rate)    (column-major, coset-major rows)
+    MerkleTreeDev tree;
+    size_t n() const { return (size_t)1 << log_n; }
+    size_t lde_n() const { return (size_t)1 << (log_n + rate_bits); }
+    int lde_bits() const { return log_n + rate_bits; }
+};
+
+// values (device, column-major ncols x n; consumed: may alias coeffs) -> batch
+void batch_from_values_dev(Batch& b, DevBuf&& values, int ncols, int log_n, int rate_bits, int cap_height);
+void batch_from_coeffs_dev(Batch& b, DevBuf&& coeffs, int ncols, int log_n, int rate_bits, int cap_height);
+
+}  // namespace zkm

@@ -1,0 +1,188 @@
+// C ABI (include/zkm_b200.h).  Every entry point catches C++ exceptions and reports them through
+// the (status, char** err) convention of the reference's own FFI (recursion/src/snark/snarks.rs:7-20).
+#include "../../include/zkm_b200.h"
+#include "batch.cuh"
+#include "poseidon.cuh"
+#include <cstring>
+#include <cstdlib>
+
+using namespace zkm;
+
+struct zkm_batch { Batch b; };
+
+static int fail(char** err, const std::exception& e) {
+    if (err) {
+        const char* w = e.what();
+        size_t n = strlen(w);
+        char* m = (char*)malloc(n + 1);
+        if (m) memcpy(m, w, n + 1);
+        *err = m;
+    }
+    return -1;
+}
+#define ZKM_API_BEGIN if (err) *err = nullptr; try {
+#define ZKM_API_END } catch (const std::exception& e) { return fail(err, e); } return 0;
+
+extern "C" {
+
+void zkm_b200_free_string(char* s) { free(s); }
+void zkm_b200_free(void* p) { free(p); }
+
+void zkm_b200_standard_fast_config(zkm_stark_config_t* c) {
+    c->rate_bits = 2; c->cap_height = 4; c->pow_bits = 16; c->num_queries = 37;
+    c->num_challenges = 2; c->arity_bits = 4; c->final_poly_bits = 5;
+}
+
+int zkm_b200_init(int device, char** err) {
+    ZKM_API_BEGIN
+    ctx_init(device);
+    ZKM_API_END
+}
+int zkm_b200_shutdown(char** err) {
+    ZKM_API_BEGIN
+    ctx_shutdown();
+    ZKM_API_END
+}
+uint64_t zkm_b200_launch_count(void) { return g_launch_count; }
+int zkm_b200_sync(char** err) {
+    ZKM_API_BEGIN
+    ZKM_CUDA(cudaStreamSynchronize(ctx().stream));
+    ZKM_API_END
+}
+
+static DevBuf upload_table(const zkm_table_t* t) {
+    Ctx& c = ctx();
+    ZKM_CHECK(t && t->cols && t->ncols > 0, "null/empty table");
+    size_t n = (size_t)1 << t->log_n;
+    DevBuf d((size_t)t->ncols * n, c.stream);
+    for (uint32_t i = 0; i < t->ncols; i++) {
+        ZKM_CHECK(t->cols[i] != nullptr, "null column pointer");
+        d.upload(t->cols[i], n, (size_t)i * n);
+    }
+    return d;
+}
+
+int zkm_b200_commit_values(const zkm_table_t* table, uint32_t rate_bits, uint32_t cap_height, zkm_batch_t** out,
+                           uint64_t* cap_out, char** err) {
+    ZKM_API_BEGIN
+    DevBuf d = upload_table(table);
+    auto* h = new zkm_batch;
+    try {
+        batch_from_values_dev(h->b, std::move(d), table->ncols, table->log_n, rate_bits, cap_height);
+    } catch (...) { delete h; throw; }
+    if (cap_out) memcpy(cap_out, h->b.tree.cap.data(), h->b.tree.cap.size() * sizeof(u64));
+    *out = h;
+    ZKM_API_END
+}
+
+int zkm_b200_commit_coeffs(const zkm_table_t* table, uint32_t rate_bits, uint32_t cap_height, zkm_batch_t** out,
+                           uint64_t* cap_out, char** err) {
+    ZKM_API_BEGIN
+    DevBuf d = upload_table(table);
+    auto* h = new zkm_batch;
+    try {
+        batch_from_coeffs_dev(h->b, std::move(d), table->ncols, table->log_n, rate_bits, cap_height);
+    } catch (...) { delete h; throw; }
+    if (cap_out) memcpy(cap_out, h->b.tree.cap.data(), h->b.tree.cap.size() * sizeof(u64));
+    *out = h;
+    ZKM_API_END
+}
+
+int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint32_t log_n, uint32_t rate_bits,
+                                  uint32_t cap_height, zkm_batch_t** out, uint64_t* cap_out, char** err) {
+    ZKM_API_BEGIN
+    Ctx& c = ctx();
+    size_t n = (size_t)1 << log_n;
+    DevBuf d((size_t)ncols * n, c.stream);
+    ZKM_CUDA(cudaMemcpyAsync(d.p, d_values, (size_t)ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream));
+    auto* h = new zkm_batch;
+    try {
+        batch_from_values_dev(h->b, std::move(d), ncols, log_n, rate_bits, cap_height);
+    } catch (...) { delete h; throw; }
+    if (cap_out) memcpy(cap_out, h->b.tree.cap.data(), h->b.tree.cap.size() * sizeof(u64));
+    *out = h;
+    ZKM_API_END
+}
+
+void zkm_b200_batch_free(zkm_batch_t* b) {
+    if (!b) return;
+    try { if (ctx_ready()) cudaStreamSynchronize(ctx().stream); } catch (...) {}
+    delete b;
+}
+
+int zkm_b200_batch_get_coeffs(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(b && (int)col < b->b.ncols, "bad batch/column");
+    b->b.coeffs.download(out, b->b.n(), (size_t)col * b->b.n());
+    ZKM_API_END
+}
+
+int zkm_b200_batch_get_lde(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(b && (int)col < b->b.ncols, "bad batch/column");
+    const Batch& B = b->b;
+    size_t N = B.lde_n(), n = B.n();
+    std::vector<u64> tmp(N);
+    B.lde.download(tmp.data(), N, (size_t)col * N);
+    int R = 1 << B.rate_bits;
+    for (int j = 0; j < R; j++)
+        for (size_t i = 0; i < n; i++) out[(i << B.rate_bits) | j] = tmp[(size_t)j * n + i];
+    ZKM_API_END
+}
+
+int zkm_b200_batch_open(const zkm_batch_t* b, uint32_t leaf_index, uint64_t* leaf_out, uint64_t* siblings_out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(b, "null batch");
+    const Batch& B = b->b;
+    Ctx& c = ctx();
+    ZKM_CHECK(leaf_index < B.lde_n(), "leaf index out of range");
+    int path_len = B.tree.log_leaves - B.tree.cap_height;
+    DevBuf idx(1, c.stream), rows(B.ncols, c.stream), path(path_len * 4 + 1, c.stream);
+    u64 hidx = leaf_index;   // low 32 bits read as u32 on device (little endian)
+    idx.upload(&hidx, 1);
+    lde_gather_rows(B.lde.p, B.lde_n(), B.ncols, B.log_n, B.rate_bits, (const u32*)idx.p, 1, rows.p, c.stream);
+    merkle_gather_paths(B.tree, (const u32*)idx.p, 1, path.p, c.stream);
+    rows.download(leaf_out, B.ncols);
+    if (path_len) path.download(siblings_out, (size_t)path_len * 4);
+    ZKM_API_END
+}
+
+int zkm_b200_ntt(uint64_t* data, uint32_t ncols, uint32_t log_n, int kind, char** err) {
+    ZKM_API_BEGIN
+    Ctx& c = ctx();
+    size_t n = (size_t)1 << log_n;
+    DevBuf d((size_t)ncols * n, c.stream);
+    d.upload(data, (size_t)ncols * n);
+    if (kind == 0) ntt_forward(c.ntt, d.p, n, d.p, n, ncols, log_n, c.stream);
+    else if (kind == 1) ntt_inverse(c.ntt, d.p, n, d.p, n, ncols, log_n, c.stream);
+    else if (kind == 2) coset_intt(c.ntt, d.p, n, d.p, n, ncols, log_n, c.stream);
+    else throw std::runtime_error("unknown transform kind");
+    d.download(data, (size_t)ncols * n);
+    ZKM_API_END
+}
+
+__global__ void poseidon_states_kernel(u64* st, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = st[i * 12 + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) st[i * 12 + k] = s[k];
+}
+
+int zkm_b200_poseidon_permute(uint64_t* states, size_t count, char** err) {
+    ZKM_API_BEGIN
+    Ctx& c = ctx();
+    if (count) {
+        DevBuf d(count * 12, c.stream);
+        d.upload(states, count * 12);
+        poseidon_states_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(d.p, count);
+        ZKM_LAUNCHED();
+        d.download(states, count * 12);
+    }
+    ZKM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Device runtime plumbing shared by the kernels' host launchers: error handling, RAII device
+// buffers on the stream-ordered allocator, and per-size twiddle/power tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+#include "gl.cuh"
+
+namespace zkm {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define ZKM_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            throw ::zkm::CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " @" +  \
+                                   __FILE__ + ":" + std::to_string(__LINE__));                   \
+    } while (0)
+
+#define ZKM_CHECK(cond, msg)                                                                     \
+    do { if (!(cond)) throw std::runtime_error(std::string(msg)); } while (0)
+
+// Count of kernel launches issued by this library (bench.py reports it as gpu_launches).
+extern unsigned long long g_launch_count;
+#define ZKM_LAUNCHED() do { ++::zkm::g_launch_count; ZKM_CUDA(cudaGetLastError()); } while (0)
+
+struct DevBuf {
+    u64* p = nullptr;
+    size_t n = 0;            // elements (u64)
+    cudaStream_t stream = 0;
+    DevBuf() {}
+    DevBuf(size_t n_, cudaStream_t s = 0) { alloc(n_, s); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), stream(o.stream) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; stream = o.stream; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n_, cudaStream_t s = 0) {
+        release();
+        n = n_; stream = s;
+        if (n) ZKM_CUDA(cudaMallocAsync((void**)&p, n * sizeof(u64), s));
+    }
+    void release() {
+        if (p) { cudaFreeAsync(p, stream); p = nullptr; n = 0; }
+    }
+    void zero() { if (p) ZKM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(u64), stream)); }
+    void upload(const u64* h, size_t cnt, size_t off = 0) {
+        ZKM_CUDA(cudaMemcpyAsync(p + off, h, cnt * sizeof(u64), cudaMemcpyHostToDevice, stream));
+    }
+    void download(u64* h, size_t cnt, size_t off = 0) const {
+        ZKM_CUDA(cudaMemcpyAsync(h, p + off, cnt * sizeof(u64), cudaMemcpyDeviceToHost, stream));
+        ZKM_CUDA(cudaStreamSynchronize(stream));
+    }
+};
+
+// Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
+struct PowTable {
+    const u64* lo = nullptr;
+    const u64* hi = nullptr;
+    int lo_bits = 10;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ gl pow_lookup(const PowTable& t, u64 e) {
+    gl l(t.lo[e & ((1u << t.lo_bits) - 1)]);
+    u64 h = e >> t.lo_bits;
+    if (h == 0) return l;
+    return l * gl(t.hi[h]);
+}
+#endif
+
+struct PowTableOwner {
+    DevBuf lo, hi;
+    PowTable view;
+};
+// Builds (on the host, uploads) the table for base g covering exponents < 2^max_bits.
+std::shared_ptr<PowTableOwner> make_pow_table(gl g, int max_bits, cudaStream_t s);
+
+}  // namespace zkm

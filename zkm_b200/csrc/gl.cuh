@@ -1,0 +1,143 @@
+// Goldilocks field p = 2^64 - 2^32 + 1 and its quadratic extension F_p[X]/(X^2 - 7), host+device.
+// Replaces the reference's use of plonky2_field::goldilocks_field::GoldilocksField and
+// extension::quadratic::QuadraticExtension (call sites: reference prover/src/prover.rs:141-789).
+// Representation: a u64 that is ALWAYS canonical (< p) at rest, so that buffers compare bit-exactly
+// with the reference's `to_canonical_u64()` view.  Montgomery form is not used:
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p) give a shift/add reduction of the 128-bit product.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ZKM_HD __host__ __device__ __forceinline__
+#define ZKM_D __device__ __forceinline__
+#else
+#define ZKM_HD inline
+#define ZKM_D inline
+#endif
+
+namespace zkm {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+static const u64 GL_P = 0xFFFFFFFF00000001ULL;
+static const u64 GL_EPS = 0xFFFFFFFFULL;
+
+struct gl {
+    u64 v;
+    ZKM_HD gl() : v(0) {}
+    ZKM_HD explicit gl(u64 x) : v(x) {}              // caller guarantees x < p
+    static ZKM_HD gl from_u64(u64 x) { return gl(x >= GL_P ? x - GL_P : x); }
+    static ZKM_HD gl zero() { return gl(0); }
+    static ZKM_HD gl one() { return gl(1); }
+};
+
+ZKM_HD gl operator+(gl a, gl b) {
+    u64 s = a.v + b.v;
+    // a,b < p: true sum < 2p; wrapped iff s < a.v
+    if (s < a.v || s >= GL_P) s -= GL_P;
+    return gl(s);
+}
+ZKM_HD gl operator-(gl a, gl b) {
+    u64 d = a.v - b.v;
+    if (a.v < b.v) d += GL_P;
+    return gl(d);
+}
+ZKM_HD gl operator-(gl a) { return gl(a.v ? GL_P - a.v : 0); }
+
+// (hi:lo) mod p, canonical.
+ZKM_HD u64 gl_reduce128(u64 lo, u64 hi) {
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t0 = lo - hh;
+    if (lo < hh) t0 -= GL_EPS;
+    u64 t1 = hl * GL_EPS;
+    u64 r = t0 + t1;
+    if (r < t1) r += GL_EPS;
+    if (r >= GL_P) r -= GL_P;
+    return r;
+}
+// (x2:x1:x0 as 32|64 bits) i.e. lo + hi32*2^64, mod p, canonical
+ZKM_HD u64 gl_reduce96(u64 lo, u32 hi32) {
+    u64 t1 = (u64)hi32 * GL_EPS;
+    u64 r = lo + t1;
+    if (r < t1) r += GL_EPS;
+    if (r >= GL_P) r -= GL_P;
+    return r;
+}
+
+ZKM_HD gl operator*(gl a, gl b) {
+#ifdef __CUDA_ARCH__
+    u64 lo = a.v * b.v;
+    u64 hi = __umul64hi(a.v, b.v);
+#else
+    unsigned __int128 p = (unsigned __int128)a.v * b.v;
+    u64 lo = (u64)p, hi = (u64)(p >> 64);
+#endif
+    return gl(gl_reduce128(lo, hi));
+}
+ZKM_HD gl& operator+=(gl& a, gl b) { a = a + b; return a; }
+ZKM_HD gl& operator-=(gl& a, gl b) { a = a - b; return a; }
+ZKM_HD gl& operator*=(gl& a, gl b) { a = a * b; return a; }
+ZKM_HD bool operator==(gl a, gl b) { return a.v == b.v; }
+ZKM_HD bool operator!=(gl a, gl b) { return a.v != b.v; }
+
+ZKM_HD gl gl_pow(gl b, u64 e) {
+    gl r = gl::one();
+    while (e) { if (e & 1) r = r * b; b = b * b; e >>= 1; }
+    return r;
+}
+ZKM_HD gl gl_inv(gl a) { return gl_pow(a, GL_P - 2); }
+ZKM_HD gl gl_exp2(gl a, unsigned k) { while (k--) a = a * a; return a; }
+
+static const u64 GL_GENERATOR = 7;
+static const u64 GL_POWER_OF_TWO_GENERATOR = 1753635133440165772ULL;
+ZKM_HD gl gl_root_of_unity(unsigned log_n) { return gl_exp2(gl(GL_POWER_OF_TWO_GENERATOR), 32 - log_n); }
+
+// ---- quadratic extension, W = 7 ----
+struct gl2 {
+    gl a, b;
+    ZKM_HD gl2() {}
+    ZKM_HD gl2(gl a_, gl b_) : a(a_), b(b_) {}
+    ZKM_HD explicit gl2(gl a_) : a(a_), b() {}
+    static ZKM_HD gl2 zero() { return gl2(); }
+    static ZKM_HD gl2 one() { return gl2(gl::one(), gl()); }
+};
+ZKM_HD gl2 operator+(gl2 x, gl2 y) { return gl2(x.a + y.a, x.b + y.b); }
+ZKM_HD gl2 operator-(gl2 x, gl2 y) { return gl2(x.a - y.a, x.b - y.b); }
+ZKM_HD gl2 operator-(gl2 x) { return gl2(-x.a, -x.b); }
+ZKM_HD gl2 operator*(gl2 x, gl2 y) {
+    gl bb = x.b * y.b;
+    gl seven_bb = gl(7) * bb;
+    return gl2(x.a * y.a + seven_bb, x.a * y.b + x.b * y.a);
+}
+ZKM_HD gl2 operator*(gl2 x, gl s) { return gl2(x.a * s, x.b * s); }
+ZKM_HD gl2 operator+(gl2 x, gl s) { return gl2(x.a + s, x.b); }
+ZKM_HD gl2 operator-(gl2 x, gl s) { return gl2(x.a - s, x.b); }
+ZKM_HD gl2& operator+=(gl2& x, gl2 y) { x = x + y; return x; }
+ZKM_HD gl2& operator-=(gl2& x, gl2 y) { x = x - y; return x; }
+ZKM_HD gl2& operator*=(gl2& x, gl2 y) { x = x * y; return x; }
+ZKM_HD bool operator==(gl2 x, gl2 y) { return x.a == y.a && x.b == y.b; }
+ZKM_HD bool operator!=(gl2 x, gl2 y) { return !(x == y); }
+ZKM_HD gl2 gl2_inv(gl2 x) {
+    gl norm = x.a * x.a - gl(7) * (x.b * x.b);
+    gl ni = gl_inv(norm);
+    return gl2(x.a * ni, -(x.b * ni));
+}
+ZKM_HD gl2 gl2_pow(gl2 b, u64 e) {
+    gl2 r = gl2::one();
+    while (e) { if (e & 1) r = r * b; b = b * b; e >>= 1; }
+    return r;
+}
+ZKM_HD gl2 gl2_exp2(gl2 a, unsigned k) { while (k--) a = a * a; return a; }
+
+ZKM_HD u32 bitrev32(u32 x, unsigned bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    u32 r = 0;
+    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+#endif
+}
+
+}  // namespace zkm

@@ -1,0 +1,174 @@
+// Poseidon Merkle-cap commitment kernels.  Replaces plonky2's MerkleTree::new(leaves, cap_height)
+// as reached from PolynomialBatch::from_values/from_coeffs (reference prover/src/prover.rs:154-163,
+// 514-521,576-587) and the per-fold trees inside prove_openings (:621).
+//   leaf   = hash_or_noop(row): <= 4 elements copied (zero padded), else Poseidon overwrite-mode
+//            sponge, rate 8, output state[0..4)            
+//   node   = Poseidon compress(left, right)
+//   cap[i] = root of the i-th contiguous block of leaves   (Appendix A.5)
+// One thread owns one 12-word sponge state in registers.  The LDE stays column-major (coalesced
+// across the warp for every column); the row-major leaf matrix of the reference is never built.
+#include "merkle.cuh"
+#include "poseidon.cuh"
+
+namespace zkm {
+
+__device__ __forceinline__ size_t lde_pos_of_leaf(u32 leaf, int log_n, int rate_bits) {
+    u32 m = bitrev32(leaf, log_n + rate_bits);
+    u32 j = m & ((1u << rate_bits) - 1), i = m >> rate_bits;
+    return ((size_t)j << log_n) + i;
+}
+
+__global__ void __launch_bounds__(128) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
+                                                            int rate_bits, u64* __restrict__ dig) {
+    const size_t N = (size_t)1 << (log_n + rate_bits);
+    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    // position -> natural index -> leaf index
+    u32 j = (u32)(pos >> log_n), i = (u32)(pos & (((size_t)1 << log_n) - 1));
+    u32 m = (i << rate_bits) | j;
+    u32 leaf = bitrev32(m, log_n + rate_bits);
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    const u64* col = lde + pos;
+    if (ncols <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (k < ncols) s[k] = col[(size_t)k * cs];
+    } else {
+        int c = 0;
+        for (; c + 8 <= ncols; c += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = __ldg(col + (size_t)(c + k) * cs);
+            poseidon_permute(s);
+        }
+        if (c < ncols) {
+            int rem = ncols - c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < rem) s[k] = __ldg(col + (size_t)(c + k) * cs);
+            poseidon_permute(s);
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + (size_t)leaf * 4);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+__global__ void __launch_bounds__(128) rows_leaf_hash_kernel(const u64* __restrict__ rows, int width, size_t num_leaves,
+                                                             u64* __restrict__ dig) {
+    size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= num_leaves) return;
+    const u64* row = rows + leaf * (size_t)width;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    if (width <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (k < width) s[k] = row[k];
+    } else {
+        int c = 0;
+        for (; c + 8 <= width; c += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = row[c + k];
+            poseidon_permute(s);
+        }
+        if (c < width) {
+            int rem = width - c;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < rem) s[k] = row[c + k];
+            poseidon_permute(s);
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + leaf * 4);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+__global__ void __launch_bounds__(128) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parents) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
+    ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
+    u64 s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
+    poseidon_permute(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(parent + i * 4);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t s) {
+    ZKM_CHECK(cap_height <= log_leaves, "Merkle cap height exceeds tree height");
+    t.log_leaves = log_leaves; t.cap_height = cap_height;
+    t.level_off.clear();
+    size_t off = 0;
+    for (int l = 0; l <= log_leaves - cap_height; l++) {
+        t.level_off.push_back(off);
+        off += ((size_t)1 << (log_leaves - l)) * 4;
+    }
+    t.digests.alloc(off, s);
+}
+
+void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
+    for (int l = 1; l < t.num_levels(); l++) {
+        size_t np = (size_t)1 << (t.log_leaves - l);
+        unsigned blocks = (unsigned)((np + 127) / 128);
+        merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+        ZKM_LAUNCHED();
+    }
+    size_t ncap = (size_t)4 << t.cap_height;
+    t.cap.resize(ncap);
+    ZKM_CUDA(cudaMemcpyAsync(t.cap.data(), t.digests.p + t.level_off.back(), ncap * sizeof(u64), cudaMemcpyDeviceToHost, s));
+    ZKM_CUDA(cudaStreamSynchronize(s));
+}
+
+void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s) {
+    size_t N = (size_t)1 << (log_n + rate_bits);
+    unsigned blocks = (unsigned)((N + 127) / 128);
+    lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests);
+    ZKM_LAUNCHED();
+}
+
+void rows_leaf_hash(const u64* rows, int width, size_t num_leaves, u64* leaf_digests, cudaStream_t s) {
+    unsigned blocks = (unsigned)((num_leaves + 127) / 128);
+    rows_leaf_hash_kernel<<<blocks, 128, 0, s>>>(rows, width, num_leaves, leaf_digests);
+    ZKM_LAUNCHED();
+}
+
+struct LevelOffsets { size_t off[40]; };
+
+__global__ void gather_paths_kernel(const u64* __restrict__ dig, LevelOffsets lo, int path_len, const u32* __restrict__ idx, int nq,
+                                    u64* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * path_len * 4) return;
+    int w = t & 3, l = (t >> 2) % path_len, q = (t >> 2) / path_len;
+    size_t node = ((size_t)idx[q] >> l) ^ 1;
+    out[t] = dig[lo.off[l] + node * 4 + w];
+}
+
+void merkle_gather_paths(const MerkleTreeDev& t, const u32* d_idx, int nq, u64* d_out, cudaStream_t s) {
+    int path_len = t.log_leaves - t.cap_height;
+    if (path_len == 0 || nq == 0) return;
+    LevelOffsets lo;
+    for (int l = 0; l < path_len; l++) lo.off[l] = t.level_off[l];
+    int total = nq * path_len * 4;
+    gather_paths_kernel<<<(total + 255) / 256, 256, 0, s>>>(t.digests.p, lo, path_len, d_idx, nq, d_out);
+    ZKM_LAUNCHED();
+}
+
+__global__ void gather_rows_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n, int rate_bits,
+                                   const u32* __restrict__ idx, int nq, u64* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * ncols) return;
+    int q = t / ncols, c = t - q * ncols;
+    size_t pos = lde_pos_of_leaf(idx[q], log_n, rate_bits);
+    out[t] = lde[(size_t)c * cs + pos];
+}
+
+void lde_gather_rows(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, const u32* d_idx, int nq, u64* d_out,
+                     cudaStream_t s) {
+    int total = nq * ncols;
+    if (!total) return;
+    gather_rows_kernel<<<(total + 255) / 256, 256, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, d_idx, nq, d_out);
+    ZKM_LAUNCHED();
+}
+
+}  // namespace zkm

@@ -1,0 +1,294 @@
+// Batched Goldilocks NTT / inverse NTT / coset low-degree extension on column-major buffers.
+// Replaces plonky2's per-column fft/ifft/coset_fft as reached from the reference's
+// PolynomialBatch::from_values / from_coeffs call sites (prover/src/prover.rs:154-163,514-521,
+// 576-587) and coset_ifft (:787).  Results are mathematically the same transforms, so outputs are
+// bit-identical canonical field elements.
+//
+// Layout: a column is n contiguous u64.  A size-n transform (n = n1*n2) runs as two shared-memory
+// passes, natural order in -> natural order out:
+//   pass A  tile = n1 strided points x T consecutive i2   (loads/stores T*8-byte contiguous runs)
+//           optional coset pre-scale, radix-2 DIF over i1, inter-pass twiddle w_n^(i2*k1)
+//   pass B  tile = T consecutive k1 rows x n2 contiguous points, DIF over i2, transposed store
+//           out[k1 + n1*k2]  (T*8-byte contiguous runs)
+// n <= 2^12 runs as a single pass with T columns per CTA.
+// The LDE onto 7*H_{4n} is four independent size-n coset transforms (shift 7*w_{4n}^j); the output is
+// kept "coset-major": LDE natural index m = 4i + j lives at lde[j*n + i].
+#include "ntt.cuh"
+#include "dev.cuh"
+#include <mutex>
+
+namespace zkm {
+
+unsigned long long g_launch_count = 0;
+
+std::shared_ptr<PowTableOwner> make_pow_table(gl g, int max_bits, cudaStream_t s) {
+    auto o = std::make_shared<PowTableOwner>();
+    int lo_bits = max_bits < 10 ? max_bits : 10;
+    size_t nlo = (size_t)1 << lo_bits;
+    size_t nhi = max_bits > lo_bits ? ((size_t)1 << (max_bits - lo_bits)) : 1;
+    std::vector<u64> lo(nlo), hi(nhi);
+    gl cur = gl::one();
+    for (size_t i = 0; i < nlo; i++) { lo[i] = cur.v; cur = cur * g; }
+    gl step = cur;  // g^(2^lo_bits)
+    cur = gl::one();
+    for (size_t i = 0; i < nhi; i++) { hi[i] = cur.v; cur = cur * step; }
+    o->lo.alloc(nlo, s); o->lo.upload(lo.data(), nlo);
+    o->hi.alloc(nhi, s); o->hi.upload(hi.data(), nhi);
+    ZKM_CUDA(cudaStreamSynchronize(s));
+    o->view.lo = o->lo.p; o->view.hi = o->hi.p; o->view.lo_bits = lo_bits;
+    return o;
+}
+
+struct NttPassParams {
+    const u64* in; u64* out;
+    size_t in_c, in_b, in_r, in_t, in_z;
+    size_t out_c, out_b, out_r, out_t, out_z;
+    int T;                        // tile width (independent transforms per CTA)
+    int ncols_total;              // valid range for the "t = column" single-pass mode
+    int t_is_column;              // single-pass mode: t indexes columns; guard against ncols
+    int load_t_fast, store_t_fast;
+    PowTable pre[4]; int has_pre; size_t pre_b, pre_r, pre_t;     // input scale  pre[z]^(b*pre_b+r*pre_r+t*pre_t)
+    PowTable post; int has_post; size_t post_b, post_t;           // output scale post^((b*post_b+t*post_t)*k)
+    u64 scale;                    // constant output multiplier (1 = none)
+    const u64* tw;                // w_R^k, k < R/2
+};
+
+template <int LOG_R>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+    constexpr int R = 1 << LOG_R;
+    extern __shared__ u64 smem[];
+    const int T = p.T, TS = T + 1;
+    u64* tw = smem;                    // R/2 (at least 1)
+    u64* x = smem + (R / 2 > 0 ? R / 2 : 1);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const size_t b = blockIdx.x, c = blockIdx.y, z = blockIdx.z;
+    for (int i = tid; i < R / 2; i += nth) tw[i] = p.tw[i];
+    const u64* in = p.in + c * p.in_c + b * p.in_b + z * p.in_z;
+    u64* out = p.out + c * p.out_c + b * p.out_b + z * p.out_z;
+    const int total = R * T;
+    int tmax = T;
+    if (p.t_is_column) { int rem = p.ncols_total - (int)(b * T); tmax = rem < T ? rem : T; }
+    // ---- load (+ optional coset scale) ----
+    for (int idx = tid; idx < total; idx += nth) {
+        int r, t;
+        if (p.load_t_fast) { r = idx / T; t = idx - r * T; } else { t = idx / R; r = idx - t * R; }
+        u64 v = 0;
+        if (t < tmax) {
+            v = in[(size_t)r * p.in_r + (size_t)t * p.in_t];
+            if (p.has_pre) {
+                u64 e = b * p.pre_b + (size_t)r * p.pre_r + (size_t)t * p.pre_t;
+                v = (gl(v) * pow_lookup(p.pre[z], e)).v;
+            }
+        }
+        x[r * TS + t] = v;
+    }
+    __syncthreads();
+    // ---- radix-2 DIF over r ----
+    const int nbf = (R / 2) * T;
+#pragma unroll 1
+    for (int s = LOG_R - 1; s >= 0; s--) {
+        const int half = 1 << s;
+        for (int idx = tid; idx < nbf; idx += nth) {
+            int j = idx / T, t = idx - j * T;
+            int pos = j & (half - 1);
+            int i0 = ((j >> s) << (s + 1)) + pos;
+            gl a(x[i0 * TS + t]), bb(x[(i0 + half) * TS + t]);
+            gl w(tw[pos << (LOG_R - 1 - s)]);
+            x[i0 * TS + t] = (a + bb).v;
+            x[(i0 + half) * TS + t] = ((a - bb) * w).v;
+        }
+        __syncthreads();
+    }
+    // ---- store: frequency k sits at position bitrev(k) ----
+    const gl scale(p.scale);
+    for (int idx = tid; idx < total; idx += nth) {
+        int k, t;
+        if (p.store_t_fast) { k = idx / T; t = idx - k * T; } else { t = idx / R; k = idx - t * R; }
+        if (t >= tmax) continue;
+        gl v(x[bitrev32((u32)k, LOG_R) * TS + t]);
+        if (p.has_post) {
+            u64 e = (b * p.post_b + (size_t)t * p.post_t) * (u64)k;
+            v = v * pow_lookup(p.post, e);
+        }
+        if (p.scale != 1) v = v * scale;
+        out[(size_t)k * p.out_r + (size_t)t * p.out_t] = v.v;
+    }
+}
+
+typedef void (*ntt_kernel_t)(NttPassParams);
+static ntt_kernel_t kernel_for(int log_r) {
+    switch (log_r) {
+#define K(i) case i: return ntt_pass_kernel<i>;
+        K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12)
+#undef K
+    }
+    throw std::runtime_error("unsupported NTT radix");
+}
+
+static void launch_pass(int log_r, const NttPassParams& p, dim3 grid, cudaStream_t s) {
+    size_t R = (size_t)1 << log_r;
+    size_t smem = ((R / 2 > 0 ? R / 2 : 1) + R * (p.T + 1)) * sizeof(u64);
+    ntt_kernel_t k = kernel_for(log_r);
+    if (smem > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, s>>>(p);
+    ZKM_LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------- tables
+struct NttTables::Impl {
+    std::mutex mu;
+    // [log_n][inverse] -> powers of w_n (or w_n^-1) for exponents < n
+    std::map<std::pair<int, int>, std::shared_ptr<PowTableOwner>> roots;
+    // small per-radix twiddle arrays  w_R^k k<R/2
+    std::map<std::pair<int, int>, std::shared_ptr<DevBuf>> tw;
+    // coset shift tables: key (log_n, rate_bits, j, inverse)
+    std::map<std::tuple<int, int, int, int>, std::shared_ptr<PowTableOwner>> shifts;
+};
+NttTables::NttTables() : impl(new Impl) {}
+NttTables::~NttTables() { delete impl; }
+
+static std::shared_ptr<PowTableOwner> get_roots(NttTables& T, int log_n, int inverse, cudaStream_t s) {
+    std::lock_guard<std::mutex> g(T.impl->mu);
+    auto key = std::make_pair(log_n, inverse);
+    auto it = T.impl->roots.find(key);
+    if (it != T.impl->roots.end()) return it->second;
+    gl w = gl_root_of_unity(log_n);
+    if (inverse) w = gl_inv(w);
+    auto t = make_pow_table(w, log_n, s);
+    T.impl->roots[key] = t;
+    return t;
+}
+static const u64* get_tw(NttTables& T, int log_r, int inverse, cudaStream_t s) {
+    std::lock_guard<std::mutex> g(T.impl->mu);
+    auto key = std::make_pair(log_r, inverse);
+    auto it = T.impl->tw.find(key);
+    if (it != T.impl->tw.end()) return it->second->p;
+    size_t half = log_r ? ((size_t)1 << (log_r - 1)) : 1;
+    std::vector<u64> h(half);
+    gl w = gl_root_of_unity(log_r);
+    if (inverse) w = gl_inv(w);
+    gl cur = gl::one();
+    for (size_t i = 0; i < half; i++) { h[i] = cur.v; cur = cur * w; }
+    auto b = std::make_shared<DevBuf>(half, s);
+    b->upload(h.data(), half);
+    ZKM_CUDA(cudaStreamSynchronize(s));
+    T.impl->tw[key] = b;
+    return b->p;
+}
+// powers of shift^(+-1) where shift = base * w_{n*2^rate_bits}^j
+static std::shared_ptr<PowTableOwner> get_shift(NttTables& T, int log_n, int rate_bits, int j, int inverse, cudaStream_t s) {
+    std::lock_guard<std::mutex> g(T.impl->mu);
+    auto key = std::make_tuple(log_n, rate_bits, j, inverse);
+    auto it = T.impl->shifts.find(key);
+    if (it != T.impl->shifts.end()) return it->second;
+    gl sh = gl(GL_GENERATOR) * gl_pow(gl_root_of_unity(log_n + rate_bits), (u64)j);
+    if (inverse) sh = gl_inv(sh);
+    auto t = make_pow_table(sh, log_n, s);
+    T.impl->shifts[key] = t;
+    return t;
+}
+
+// Split log_n into (log_n1, log_n2) and choose the tile width.
+static void plan(int log_n, int& l1, int& l2, int& T) {
+    if (log_n <= 12) { l1 = log_n; l2 = 0; T = (1 << 12) >> log_n; if (T > 16) T = 16; if (T < 1) T = 1; return; }
+    l2 = log_n / 2; l1 = log_n - l2;
+    int lmax = l1;   // l1 >= l2
+    T = (1 << 14) >> lmax;      // <= 16384 elements (131 KB + pad) per tile
+    if (T > 16) T = 16;
+    if (T < 2) T = 2;
+}
+
+// One size-n transform per (column, z).  shifts: optional pre-scale tables per z (coset).
+static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_zs, u64* out, size_t out_cs, size_t out_zs,
+                        int ncols, int nz, int log_n, int inverse, const PowTable* pre, u64 final_scale, cudaStream_t s) {
+    if (ncols == 0) return;
+    int l1, l2, T;
+    plan(log_n, l1, l2, T);
+    size_t n = (size_t)1 << log_n;
+    NttPassParams p = {};
+    p.has_pre = pre != nullptr;
+    if (pre) for (int z = 0; z < nz; z++) p.pre[z] = pre[z];
+    if (l2 == 0) {
+        // single pass; t indexes columns
+        p.in = in; p.out = out;
+        p.in_c = 0; p.in_b = (size_t)T * in_cs; p.in_r = 1; p.in_t = in_cs; p.in_z = in_zs;
+        p.out_c = 0; p.out_b = (size_t)T * out_cs; p.out_r = 1; p.out_t = out_cs; p.out_z = out_zs;
+        p.T = T; p.t_is_column = 1; p.ncols_total = ncols;
+        p.load_t_fast = 0; p.store_t_fast = 0;
+        p.pre_b = 0; p.pre_r = 1; p.pre_t = 0;
+        p.has_post = 0; p.scale = final_scale;
+        p.tw = get_tw(tabs, l1, inverse, s);
+        dim3 grid((ncols + T - 1) / T, 1, nz);
+        launch_pass(l1, p, grid, s);
+        return;
+    }
+    size_t n1 = (size_t)1 << l1, n2 = (size_t)1 << l2;
+    auto roots = get_roots(tabs, log_n, inverse, s);
+    const u64* twA = get_tw(tabs, l1, inverse, s);
+    const u64* twB = get_tw(tabs, l2, inverse, s);
+    // Column chunks sized so the inter-pass scratch (pass A output) stays L2-resident (~64 MB).
+    size_t per_col = (size_t)nz * n * sizeof(u64);
+    int chunk = (int)((64u << 20) / per_col);
+    if (chunk < 1) chunk = 1;
+    if (chunk > ncols) chunk = ncols;
+    DevBuf scratch((size_t)chunk * nz * n, s);
+    for (int c0 = 0; c0 < ncols; c0 += chunk) {
+        int nc = ncols - c0 < chunk ? ncols - c0 : chunk;
+        // pass A: in -> scratch[(c*nz+z)*n + k1*n2 + i2], strided radix-n1 transforms
+        p.in = in + (size_t)c0 * in_cs; p.out = scratch.p;
+        p.in_c = in_cs; p.in_b = T; p.in_r = n2; p.in_t = 1; p.in_z = in_zs;
+        p.out_c = (size_t)nz * n; p.out_b = T; p.out_r = n2; p.out_t = 1; p.out_z = n;
+        p.T = T; p.t_is_column = 0; p.ncols_total = nc;
+        p.load_t_fast = 1; p.store_t_fast = 1;
+        p.pre_b = T; p.pre_r = n2; p.pre_t = 1;
+        p.post = roots->view; p.has_post = 1; p.post_b = T; p.post_t = 1;
+        p.scale = 1;
+        p.tw = twA;
+        launch_pass(l1, p, dim3((unsigned)(n2 / T), nc, nz), s);
+        // pass B: scratch rows k1 (contiguous i2) -> out[k1 + n1*k2]
+        NttPassParams q = {};
+        q.in = scratch.p; q.out = out + (size_t)c0 * out_cs;
+        q.in_c = (size_t)nz * n; q.in_b = (size_t)T * n2; q.in_r = 1; q.in_t = n2; q.in_z = n;
+        q.out_c = out_cs; q.out_b = T; q.out_r = n1; q.out_t = 1; q.out_z = out_zs;
+        q.T = T; q.t_is_column = 0; q.ncols_total = nc;
+        q.load_t_fast = 0; q.store_t_fast = 1;
+        q.has_pre = 0; q.has_post = 0; q.scale = final_scale;
+        q.tw = twB;
+        launch_pass(l2, q, dim3((unsigned)(n1 / T), nc, nz), s);
+    }
+}
+
+void ntt_forward(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s) {
+    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 0, nullptr, 1, s);
+}
+void ntt_inverse(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s) {
+    gl ninv = gl_inv(gl((u64)1 << log_n));
+    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 1, nullptr, ninv.v, s);
+}
+void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t out_cs, int ncols, int log_n, int rate_bits,
+               cudaStream_t s) {
+    ZKM_CHECK(rate_bits <= 2, "rate_bits > 2 unsupported");
+    int nz = 1 << rate_bits;
+    PowTable pre[4];
+    std::shared_ptr<PowTableOwner> keep[4];
+    for (int j = 0; j < nz; j++) { keep[j] = get_shift(t, log_n, rate_bits, j, 0, s); pre[j] = keep[j]->view; }
+    ntt_generic(t, coeffs, in_cs, 0, lde, out_cs, (size_t)1 << log_n, ncols, nz, log_n, 0, pre, 1, s);
+}
+
+// values on the coset 7*H_n (natural order) -> coefficients:  ifft then scale coefficient i by 7^-i.
+__global__ void scale_pow_kernel(u64* data, size_t cs, size_t n, PowTable tab) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64* col = data + (size_t)blockIdx.y * cs;
+    col[i] = (gl(col[i]) * pow_lookup(tab, i)).v;
+}
+void coset_intt(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s) {
+    ntt_inverse(t, in, in_cs, out, out_cs, ncols, log_n, s);
+    auto sh = get_shift(t, log_n, 0, 0, 1, s);   // powers of 7^-1
+    size_t n = (size_t)1 << log_n;
+    dim3 grid((unsigned)((n + 255) / 256), ncols);
+    scale_pow_kernel<<<grid, 256, 0, s>>>(out, out_cs, n, sh->view);
+    ZKM_LAUNCHED();
+}
+
+}  // namespace zkm

@@ -1,0 +1,107 @@
+"""ctypes binding of include/zkm_b200.h."""
+import ctypes as C
+import pathlib
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libzkm_b200.so"
+
+P = 0xFFFFFFFF00000001
+
+
+class ZkmError(RuntimeError):
+    pass
+
+
+class Table(C.Structure):
+    _fields_ = [("cols", C.POINTER(C.POINTER(C.c_uint64))), ("ncols", C.c_uint32), ("log_n", C.c_uint32)]
+
+
+class StarkConfig(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("rate_bits", "cap_height", "pow_bits", "num_queries", "num_challenges", "arity_bits", "final_poly_bits")]
+
+
+_lib = None
+
+# every symbol include/zkm_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "zkm_b200_free_string", "zkm_b200_free", "zkm_b200_standard_fast_config", "zkm_b200_init", "zkm_b200_shutdown",
+    "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
+    "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
+    "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute",
+]
+
+
+def load():
+    """Loads libzkm_b200.so; raises if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ZkmError(f"{LIB_PATH} not built: run `python -m zkm_b200.build` (nvcc, sm_100a). No CPU fallback exists.")
+    lib = C.CDLL(str(LIB_PATH))
+    u64p = C.POINTER(C.c_uint64)
+    errp = C.POINTER(C.c_char_p)
+    lib.zkm_b200_free_string.argtypes = [C.c_void_p]
+    lib.zkm_b200_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_shutdown.argtypes = [C.POINTER(C.c_void_p)]
+    lib.zkm_b200_sync.argtypes = [C.POINTER(C.c_void_p)]
+    lib.zkm_b200_launch_count.restype = C.c_uint64
+    lib.zkm_b200_standard_fast_config.argtypes = [C.POINTER(StarkConfig)]
+    for name in ("zkm_b200_commit_values", "zkm_b200_commit_coeffs"):
+        getattr(lib, name).argtypes = [C.POINTER(Table), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), u64p,
+                                       C.POINTER(C.c_void_p)]
+    lib.zkm_b200_commit_values_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_batch_free.argtypes = [C.c_void_p]
+    lib.zkm_b200_batch_get_coeffs.argtypes = [C.c_void_p, C.c_uint32, u64p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_batch_get_lde.argtypes = [C.c_void_p, C.c_uint32, u64p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_batch_open.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_ntt.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_poseidon_permute.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p)]
+    del errp
+    _lib = lib
+    return lib
+
+
+def check(lib, rc, err):
+    if rc != 0:
+        msg = C.cast(err, C.c_char_p).value if err.value else b"unknown error"
+        text = msg.decode(errors="replace")
+        if err.value:
+            lib.zkm_b200_free_string(err)
+        raise ZkmError(text)
+
+
+def u64ptr(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def make_table(cols: np.ndarray):
+    """cols: (ncols, n) uint64 C-contiguous -> (Table, keepalive)."""
+    assert cols.dtype == np.uint64 and cols.ndim == 2 and cols.flags["C_CONTIGUOUS"]
+    ncols, n = cols.shape
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    ptrs = (C.POINTER(C.c_uint64) * ncols)()
+    base = cols.ctypes.data
+    for i in range(ncols):
+        ptrs[i] = C.cast(base + i * n * 8, C.POINTER(C.c_uint64))
+    t = Table(C.cast(ptrs, C.POINTER(C.POINTER(C.c_uint64))), ncols, log_n)
+    return t, (ptrs, cols)
+
+
+_inited = False
+
+
+def init(device: int = 0):
+    global _inited
+    lib = load()
+    if not _inited:
+        err = C.c_void_p()
+        check(lib, lib.zkm_b200_init(device, C.byref(err)), err)
+        _inited = True
+    return lib

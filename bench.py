@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — measures the zkm STARK proving hot path on B200 (contract: task prompt ④).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload U20|U16|...]
+
+A "step" = one pass of the hot path over one synthetic segment (workload U20: the
+12 MIPS STARK tables with Arithmetic/Cpu/Memory at 2^20 rows, Logic at 2^18, the rest at 2^6).
+  value  : whole-job steps/s with the trace columns already resident in HBM (device timing, CUDA
+           events on the library's stream, max over ranks)
+  e2e    : the same through the C-ABI entry point with HOST (pinned) column buffers: H2D of every
+           trace column and D2H of the caps/proof inside the timed region
+  roofline / cpu_baseline : see DESIGN.md §Measurement
+One process per GPU; ranks prove independent segments (no data-path collective): weak scaling.
+PyTorch is used only for device/pinned memory, torch.distributed barriers and the max-over-ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# Table enum order (reference prover/src/all_stark.rs:97-110) and column counts.
+TABLES = ["Arithmetic", "Cpu", "Poseidon", "PoseidonSponge", "Keccak", "KeccakSponge", "ShaExtend",
+          "ShaExtendSponge", "ShaCompress", "ShaCompressSponge", "Logic", "Memory"]
+NCOLS = [54, 259, 262, 110, 2431, 470, 78, 76, 224, 127, 69, 13]
+
+
+def workload_log_heights(name):
+    if name.startswith("U"):
+        big = int(name[1:])
+        h = [6] * 12
+        h[0] = h[1] = h[11] = big
+        h[10] = max(6, big - 2)
+        h[0] = max(h[0], 16)           # Arithmetic >= 2^16 rows (arithmetic_stark.rs:123,178-181)
+        return h
+    raise SystemExit(f"unknown workload {name}")
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+class Segment:
+    """One synthetic segment and the hot-path step over it.
+
+    Stages currently on the GPU path are listed in `stages`; the metric names them, so a partial
+    pipeline is never reported as a full proof."""
+
+    def __init__(self, lib, workload, seed_offset=0):
+        import torch
+        from zkm_b200 import lib as zl
+        self.zl, self.lib, self.torch = zl, lib, torch
+        self.heights = workload_log_heights(workload)
+        self.stages = "a1+a2: trace commitments of the 12 tables (iNTT, coset LDE x4, Poseidon Merkle caps)"
+        self.metric = f"segment trace-commit passes/sec ({workload}; stages a1+a2 of prove_with_traces)"
+        self.unit = "segments/s"
+        self.dev = []
+        err = C.c_void_p()
+        for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
+            buf = torch.empty(nc << lg, dtype=torch.int64, device="cuda")
+            seed = (0x5EED000000000000 | (t << 16)) + (seed_offset << 32)
+            zl.check(lib, lib.zkm_b200_synth_columns_device(buf.data_ptr(), nc, lg, seed, C.byref(err)), err)
+            self.dev.append(buf)
+        self.input_bytes = sum(8 * (nc << lg) for nc, lg in zip(NCOLS, self.heights))
+        self.output_bytes = 12 * 16 * 4 * 8
+        self.host = None
+        self.caps = np.zeros((12, 64), dtype=np.uint64)
+
+    def sync(self):
+        err = C.c_void_p()
+        self.zl.check(self.lib, self.lib.zkm_b200_sync(C.byref(err)), err)
+
+    def timed(self, fn):
+        err = C.c_void_p()
+        ms = C.c_double()
+        self.zl.check(self.lib, self.lib.zkm_b200_timer_start(C.byref(err)), err)
+        fn()
+        self.zl.check(self.lib, self.lib.zkm_b200_timer_stop(C.byref(ms), C.byref(err)), err)
+        return ms.value
+
+    def step_device(self):
+        lib, zl = self.lib, self.zl
+        err = C.c_void_p()
+        for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
+            h = C.c_void_p()
+            zl.check(lib, lib.zkm_b200_commit_values_device(self.dev[t].data_ptr(), nc, lg, 2, 4, C.byref(h),
+                                                            zl.u64ptr(self.caps[t]), C.byref(err)), err)
+            lib.zkm_b200_batch_free(h)
+
+    def prepare_host(self):
+        torch = self.torch
+        self.host, self.tables = [], []
+        for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
+            hbuf = torch.empty(nc << lg, dtype=torch.int64, pin_memory=True)
+            hbuf.copy_(self.dev[t])
+            arr = hbuf.numpy().view(np.uint64).reshape(nc, 1 << lg)
+            self.host.append(hbuf)
+            self.tables.append(self.zl.make_table(arr))
+        torch.cuda.synchronize()
+
+    def step_e2e(self):
+        lib, zl = self.lib, self.zl
+        err = C.c_void_p()
+        for t in range(12):
+            h = C.c_void_p()
+            zl.check(lib, lib.zkm_b200_commit_values(C.byref(self.tables[t][0]), 2, 4, C.byref(h),
+                                                     zl.u64ptr(self.caps[t]), C.byref(err)), err)
+            lib.zkm_b200_batch_free(h)
+
+    def profile_reset(self):
+        err = C.c_void_p()
+        self.zl.check(self.lib, self.lib.zkm_b200_profile_reset(C.byref(err)), err)
+
+    def profile_families(self):
+        lib = self.lib
+        ptr = lib.zkm_b200_profile_families()
+        names = C.cast(ptr, C.c_char_p).value.decode().split("\n") if ptr else []
+        lib.zkm_b200_free_string(ptr)
+        out = {}
+        for n in filter(None, names):
+            ms, la, by, err = C.c_double(), C.c_uint64(), C.c_double(), C.c_void_p()
+            self.zl.check(lib, lib.zkm_b200_profile_get(n.encode(), C.byref(ms), C.byref(la), C.byref(by), C.byref(err)), err)
+            out[n] = {"ms": ms.value, "launches": la.value, "bytes": by.value}
+        return out
+
+    @staticmethod
+    def ncu_traffic(family):
+        """dram bytes per launch from the committed `ncu --set full` capture (profiles/*.json), or None."""
+        f = ROOT / "profiles" / "ncu_traffic.json"
+        if f.exists():
+            return json.loads(f.read_text()).get(family)
+        return None
+
+
+def cpu_pass(workload, ncores, sample_only=False):
+    """CPU arm: the restated oracle (oracle/liborc.so, `kind: port`) on a bounded sample of the workload:
+    the same 12 tables with every height above 2^16 cut to 2^16, timed on all host cores; the result
+    is scaled linearly in rows back to the full workload (this favours the CPU: it ignores the log n
+    factor of the transforms)."""
+    from oracle import binding
+    orc = binding.load()
+    orc.orc_set_threads(ncores)
+    full = workload_log_heights(workload)
+    sample = [min(h, 16) for h in full]
+    if sample_only:
+        sample = [min(h, 10) for h in full]
+    rows_full = sum(nc << lg for nc, lg in zip(NCOLS, full))
+    rows_s = sum(nc << lg for nc, lg in zip(NCOLS, sample))
+    rng = np.random.default_rng(1)
+    t_total = 0.0
+    cap = np.zeros(64, dtype=np.uint64)
+    for nc, lg in zip(NCOLS, sample):
+        cols = (rng.integers(0, 2**63, size=(nc, 1 << lg), dtype=np.uint64) % np.uint64(0xFFFFFFFF00000001))
+        ptrs = binding.col_ptrs(cols)
+        t0 = time.perf_counter()
+        h = orc.orc_commit(ptrs, nc, lg, 2, 4, 1, binding.u64ptr(cap))
+        t_total += time.perf_counter() - t0
+        orc.orc_batch_free(h)
+    scale = rows_full / rows_s
+    return {"value": 1.0 / (t_total * scale), "unit": "segments/s",
+            "metric": f"segment trace-commit passes/sec ({workload}; stages a1+a2 of prove_with_traces)",
+            "sample": f"heights {sample} ({t_total:.2f} s on {ncores} threads), scaled x{scale:.2f} linearly in cells to {workload}",
+            "note": "restated C++ oracle (the Rust reference cannot be built here: no cargo, plonky2 un-vendored)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The Rust reference cannot be
+    built in this image (no cargo; plonky2 un-vendored — DESIGN.md), so this times the restated C++
+    oracle on all host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    for _ in range(args.warmup and 1):
+        cpu_pass(args.workload, ncores, sample_only=True)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_pass(args.workload, ncores, sample_only=False))
+    best = max(v["value"] for v in vals)
+    info = vals[0]
+    line = {"impl": "reference", "metric": info["metric"], "value": best, "unit": info["unit"], "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / best if best else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)",
+            "data": "synthetic", "config": {"workload": args.workload, "note": info["note"]},
+            "cpu_baseline": {"value": best, "unit": info["unit"], "cores": ncores, "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": best, "unit": info["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="U20")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from zkm_b200 import lib as zl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = zl.init(local)
+    seg = Segment(lib, args.workload, seed_offset=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        seg.sync()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        seg.step_device()
+    # ---- device-resident timing ----
+    lib.zkm_b200_profile_enable(1)
+    seg.profile_reset()
+    barrier()
+    l0 = lib.zkm_b200_launch_count()
+    with ClockSampler(local) as clk:
+        t_dev = seg.timed(lambda: [seg.step_device() for _ in range(args.steps)])
+        barrier()
+    launches = lib.zkm_b200_launch_count() - l0
+    fam = seg.profile_families()
+    lib.zkm_b200_profile_enable(0)
+    # ---- end to end through the C ABI with host buffers ----
+    seg.prepare_host()
+    seg.step_e2e()
+    barrier()
+    t_e2e = seg.timed(lambda: [seg.step_e2e() for _ in range(args.steps)])
+    barrier()
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = t.tolist()
+    if rank == 0:
+        peak, peak_kind = peaks()
+        total_ms = sum(v["ms"] for v in fam.values()) or 1.0
+        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        # the roofline entry is reported for the HBM-bound NTT family (BASELINE.json: "NTT GB/s vs HBM peak") and
+        # the dominant family is named next to it
+        ntt = fam.get("ntt_pass", top[1])
+        ach = ntt["bytes"] / (ntt["ms"] * 1e-3) / 1e9 if ntt["ms"] else 0.0
+        value = args.steps * world / (t_dev * 1e-3)
+        e2e = args.steps * world / (t_e2e * 1e-3)
+        line = {"metric": seg.metric, "value": value, "unit": seg.unit, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 (Goldilocks)", "data": "synthetic",
+                "config": {"workload": args.workload, "stages": seg.stages, "log_heights": seg.heights,
+                           "l2": f"inputs {seg.input_bytes / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)",
+                           "parallelism": f"{world} independent segments (one per GPU)"},
+                "e2e": {"value": e2e, "unit": seg.unit, "ms_per_step": t_e2e / args.steps,
+                        "h2d_bytes_per_step": seg.input_bytes, "d2h_bytes_per_step": seg.output_bytes},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "peak_kind": peak_kind, "traffic": seg.ncu_traffic("ntt_pass"),
+                             "launches": ntt["launches"], "avg_launch_ms": ntt["ms"] / max(1, ntt["launches"]),
+                             "share_of_step": ntt["ms"] / total_ms},
+                "kernel_families": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                        "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0),
+                                        "share": v["ms"] / total_ms} for k, v in fam.items()},
+                "dominant_family": top[0],
+                "clocks": clk.summary()}
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_pass(args.workload, os.cpu_count() or 1, sample_only=False)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": cb["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,18 @@ uint64_t zkm_b200_launch_count(void);
 /* Blocks until all device work queued by the library has finished. */
 int zkm_b200_sync(char** err);
 
+/* CUDA-event stopwatch on the library's stream (bench.py times the whole step with it). */
+int zkm_b200_timer_start(char** err);
+int zkm_b200_timer_stop(double* ms, char** err);
+/* Device-side timing per kernel family (CUDA events on the launching stream) — the counterpart of the
+ * reference's TimingTree scopes (prover.rs:86,144-167,191-215,...).  `bytes` is the algorithmic byte
+ * count the family processed (DESIGN.md lists the per-unit figures).  families() returns a malloc'ed
+ * '\n'-separated list, released with zkm_b200_free_string. */
+void zkm_b200_profile_enable(int on);
+int zkm_b200_profile_reset(char** err);
+int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, double* bytes, char** err);
+char* zkm_b200_profile_families(void);
+
 /* ---- staged API (stage-by-stage parity against the oracle) ------------------------------- */
 
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height) — prover.rs:154-163,
@@ -73,6 +85,9 @@ int zkm_b200_commit_coeffs(const zkm_table_t* table, uint32_t rate_bits, uint32_
 int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint32_t log_n,
                                   uint32_t rate_bits, uint32_t cap_height, zkm_batch_t** out,
                                   uint64_t* cap_out, char** err);
+/* Fills a device buffer (ncols x 2^log_n u64, column-major) with the synthetic SplitMix64 columns of
+ * BASELINE.md §3 (stream seed | column index, value mod p).  Benchmark input generator. */
+int zkm_b200_synth_columns_device(uint64_t* d_out, uint32_t ncols, uint32_t log_n, uint64_t seed, char** err);
 void zkm_b200_batch_free(zkm_batch_t* b);
 /* Coefficients of polynomial `col` (2^log_n u64). */
 int zkm_b200_batch_get_coeffs(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err);

@@ -50,6 +50,47 @@ int zkm_b200_sync(char** err) {
     ZKM_API_END
 }
 
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+int zkm_b200_timer_start(char** err) {
+    ZKM_API_BEGIN
+    if (!g_t0) { ZKM_CUDA(cudaEventCreate(&g_t0)); ZKM_CUDA(cudaEventCreate(&g_t1)); }
+    ZKM_CUDA(cudaEventRecord(g_t0, ctx().stream));
+    ZKM_API_END
+}
+int zkm_b200_timer_stop(double* ms, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(g_t0, "timer not started");
+    ZKM_CUDA(cudaEventRecord(g_t1, ctx().stream));
+    ZKM_CUDA(cudaEventSynchronize(g_t1));
+    float f = 0;
+    ZKM_CUDA(cudaEventElapsedTime(&f, g_t0, g_t1));
+    *ms = f;
+    ZKM_API_END
+}
+void zkm_b200_profile_enable(int on) { prof_enable(on != 0); }
+int zkm_b200_profile_reset(char** err) {
+    ZKM_API_BEGIN
+    prof_reset();
+    ZKM_API_END
+}
+int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, double* bytes, char** err) {
+    ZKM_API_BEGIN
+    unsigned long long l = 0; double m = 0, b = 0;
+    bool ok = prof_get(family, &m, &l, &b);
+    if (ms) *ms = m;
+    if (launches) *launches = l;
+    if (bytes) *bytes = b;
+    if (!ok) throw std::runtime_error(std::string("no such kernel family: ") + family);
+    ZKM_API_END
+}
+char* zkm_b200_profile_families(void) {
+    std::string n;
+    try { n = prof_names(); } catch (...) {}
+    char* m = (char*)malloc(n.size() + 1);
+    if (m) memcpy(m, n.c_str(), n.size() + 1);
+    return m;
+}
+
 static DevBuf upload_table(const zkm_table_t* t) {
     Ctx& c = ctx();
     ZKM_CHECK(t && t->cols && t->ncols > 0, "null/empty table");
@@ -158,6 +199,30 @@ int zkm_b200_ntt(uint64_t* data, uint32_t ncols, uint32_t log_n, int kind, char*
     else if (kind == 2) coset_intt(c.ntt, d.p, n, d.p, n, ncols, log_n, c.stream);
     else throw std::runtime_error("unknown transform kind");
     d.download(data, (size_t)ncols * n);
+    ZKM_API_END
+}
+
+// SplitMix64 stream per column, reduced mod p (BASELINE.md §3 synthetic inputs): value i of column c =
+// mix(seed_c + (i+1)*0x9E3779B97F4A7C15) mod p with seed_c = seed | c.
+__global__ void synth_columns_kernel(u64* out, size_t n, u64 seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 c = blockIdx.y;
+    u64 z = (seed | c) + (u64)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    out[c * n + i] = z >= GL_P ? z - GL_P : z;
+}
+
+int zkm_b200_synth_columns_device(uint64_t* d_out, uint32_t ncols, uint32_t log_n, uint64_t seed, char** err) {
+    ZKM_API_BEGIN
+    Ctx& c = ctx();
+    size_t n = (size_t)1 << log_n;
+    dim3 grid((unsigned)((n + 255) / 256), ncols);
+    synth_columns_kernel<<<grid, 256, 0, c.stream>>>(d_out, n, seed);
+    ZKM_LAUNCHED();
+    ZKM_CUDA(cudaStreamSynchronize(c.stream));
     ZKM_API_END
 }
 

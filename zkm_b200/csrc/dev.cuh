@@ -60,6 +60,21 @@ struct DevBuf {
     }
 };
 
+// Per-kernel-family device timing (CUDA events on the launching stream), switched on by
+// zkm_b200_profile_enable.  Scope names follow the kernel families listed in DESIGN.md; bench.py
+// reads them back for the roofline entry.  Disabled: zero overhead beyond one branch.
+struct ProfScope {
+    const char* name; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; double bytes;
+    ProfScope(const char* name_, cudaStream_t s_, double algorithmic_bytes = 0);
+    ~ProfScope();
+};
+void prof_enable(bool on);
+void prof_reset();
+// Resolves pending events (synchronises) and returns totals for one family; false if never seen.
+bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes);
+// Names seen so far, '\n'-separated.
+std::string prof_names();
+
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 struct PowTable {
     const u64* lo = nullptr;

@@ -7,11 +7,10 @@
 #pragma once
 #include <stdint.h>
 
+#include "tables/hd.h"
 #ifdef __CUDACC__
-#define ZKM_HD __host__ __device__ __forceinline__
 #define ZKM_D __device__ __forceinline__
 #else
-#define ZKM_HD inline
 #define ZKM_D inline
 #endif
 

@@ -108,11 +108,14 @@ void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t
 }
 
 void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
+    {
+    ProfScope ps("merkle_levels", s, 48.0 * (double)(t.num_leaves() - ((size_t)1 << t.cap_height)));
     for (int l = 1; l < t.num_levels(); l++) {
         size_t np = (size_t)1 << (t.log_leaves - l);
         unsigned blocks = (unsigned)((np + 127) / 128);
         merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
         ZKM_LAUNCHED();
+    }
     }
     size_t ncap = (size_t)4 << t.cap_height;
     t.cap.resize(ncap);
@@ -123,12 +126,14 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
 void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s) {
     size_t N = (size_t)1 << (log_n + rate_bits);
     unsigned blocks = (unsigned)((N + 127) / 128);
+    ProfScope ps("leaf_hash", s, (double)N * (8.0 * ncols + 32.0));
     lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests);
     ZKM_LAUNCHED();
 }
 
 void rows_leaf_hash(const u64* rows, int width, size_t num_leaves, u64* leaf_digests, cudaStream_t s) {
     unsigned blocks = (unsigned)((num_leaves + 127) / 128);
+    ProfScope ps("leaf_hash_rows", s, (double)num_leaves * (8.0 * width + 32.0));
     rows_leaf_hash_kernel<<<blocks, 128, 0, s>>>(rows, width, num_leaves, leaf_digests);
     ZKM_LAUNCHED();
 }

@@ -129,6 +129,8 @@ static void launch_pass(int log_r, const NttPassParams& p, dim3 grid, cudaStream
     size_t R = (size_t)1 << log_r;
     size_t smem = ((R / 2 > 0 ? R / 2 : 1) + R * (p.T + 1)) * sizeof(u64);
     ntt_kernel_t k = kernel_for(log_r);
+    // algorithmic bytes of one pass: every element read once and written once
+    ProfScope ps("ntt_pass", s, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
     if (smem > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>(p);
     ZKM_LAUNCHED();
@@ -287,6 +289,7 @@ void coset_intt(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_
     auto sh = get_shift(t, log_n, 0, 0, 1, s);   // powers of 7^-1
     size_t n = (size_t)1 << log_n;
     dim3 grid((unsigned)((n + 255) / 256), ncols);
+    ProfScope ps("scale_pow", s, 16.0 * (double)n * ncols);
     scale_pow_kernel<<<grid, 256, 0, s>>>(out, out_cs, n, sh->view);
     ZKM_LAUNCHED();
 }

@@ -1,0 +1,69 @@
+// Device-side timing of kernel families with CUDA events on the launching stream (dev.cuh ProfScope).
+// The B200 counterpart of the reference's TimingTree scopes (prover/src/prover.rs:86,144-167,...):
+// the reference times wall-clock scopes on the host, here each kernel family is timed on the device.
+#include "dev.cuh"
+#include <map>
+#include <vector>
+#include <mutex>
+
+namespace zkm {
+
+namespace {
+struct Pending { std::string name; cudaEvent_t e0, e1; double bytes; };
+struct Total { double ms = 0; unsigned long long launches = 0; double bytes = 0; };
+bool g_on = false;
+std::vector<Pending> g_pending;
+std::vector<cudaEvent_t> g_pool;
+std::map<std::string, Total> g_totals;
+std::vector<std::string> g_order;
+
+cudaEvent_t get_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    ZKM_CUDA(cudaEventCreate(&e));
+    return e;
+}
+void resolve() {
+    for (Pending& p : g_pending) {
+        cudaEventSynchronize(p.e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.e0, p.e1);
+        auto it = g_totals.find(p.name);
+        if (it == g_totals.end()) { g_order.push_back(p.name); it = g_totals.emplace(p.name, Total()).first; }
+        it->second.ms += ms; it->second.launches++; it->second.bytes += p.bytes;
+        g_pool.push_back(p.e0); g_pool.push_back(p.e1);
+    }
+    g_pending.clear();
+}
+}  // namespace
+
+ProfScope::ProfScope(const char* name_, cudaStream_t s_, double b) : name(name_), s(s_), bytes(b) {
+    if (!g_on) return;
+    e0 = get_event(); e1 = get_event();
+    cudaEventRecord(e0, s);
+}
+ProfScope::~ProfScope() {
+    if (!e0) return;
+    cudaEventRecord(e1, s);
+    g_pending.push_back({name, e0, e1, bytes});
+    if (g_pending.size() > 8192) resolve();
+}
+void prof_enable(bool on) { g_on = on; }
+void prof_reset() { resolve(); g_totals.clear(); g_order.clear(); }
+bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes) {
+    resolve();
+    auto it = g_totals.find(name);
+    if (it == g_totals.end()) return false;
+    if (ms) *ms = it->second.ms;
+    if (launches) *launches = it->second.launches;
+    if (bytes) *bytes = it->second.bytes;
+    return true;
+}
+std::string prof_names() {
+    resolve();
+    std::string r;
+    for (auto& n : g_order) { if (!r.empty()) r += "\n"; r += n; }
+    return r;
+}
+
+}  // namespace zkm

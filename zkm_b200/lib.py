@@ -31,6 +31,7 @@ EXPORTS = [
     "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute",
+    "zkm_b200_synth_columns_device", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 
@@ -61,6 +62,13 @@ def load():
     lib.zkm_b200_batch_open.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p, C.POINTER(C.c_void_p)]
     lib.zkm_b200_ntt.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     lib.zkm_b200_poseidon_permute.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_synth_columns_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_timer_start.argtypes = [C.POINTER(C.c_void_p)]
+    lib.zkm_b200_timer_stop.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_profile_enable.argtypes = [C.c_int]
+    lib.zkm_b200_profile_reset.argtypes = [C.POINTER(C.c_void_p)]
+    lib.zkm_b200_profile_get.argtypes = [C.c_char_p, C.POINTER(C.c_double), u64p, C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_profile_families.restype = C.c_void_p
     del errp
     _lib = lib
     return lib

@@ -46,8 +46,53 @@ def load():
     lib.orc_batch_get_coeffs.argtypes = [C.c_void_p, C.c_uint32, u64p]
     lib.orc_batch_get_lde.argtypes = [C.c_void_p, C.c_uint32, u64p]
     lib.orc_batch_open.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p]
+    lib.orc_set_threads.argtypes = [C.c_int]
+    lib.orc_prove_system.restype = C.c_void_p
+    lib.orc_prove_system.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint32), C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
+    lib.orc_free.argtypes = [C.c_void_p]
+    lib.orc_verify_system.argtypes = [C.c_int, u64p, C.c_size_t, C.POINTER(C.c_uint32)]
+    lib.orc_check_table_constraints.restype = C.c_long
+    lib.orc_check_table_constraints.argtypes = [C.c_int, C.POINTER(u64p), C.c_uint32, C.c_uint32]
+    lib.orc_gen_poseidon_rows.argtypes = [u64p, u64p, C.c_size_t, u64p]
     _lib = lib
     return lib
+
+
+STANDARD_FAST_CONFIG = (2, 4, 16, 37, 2, 4, 5)     # reference prover/src/config.rs:17-29
+
+
+def tables_arg(traces):
+    """traces: list of (ncols, n) uint64 arrays -> (void* tables, ncols[], log_n[], keepalive)."""
+    T = len(traces)
+    per = [col_ptrs(t) for t in traces]
+    arr = (C.c_void_p * T)(*[C.cast(p, C.c_void_p) for p in per])
+    ncols = (C.c_uint32 * T)(*[t.shape[0] for t in traces])
+    logn = (C.c_uint32 * T)(*[t.shape[1].bit_length() - 1 for t in traces])
+    return arr, ncols, logn, (per, traces)
+
+
+def prove_system(lib, system_id, traces, roots_before=None, roots_after=None, userdata=bytes(32), cfg=STANDARD_FAST_CONFIG):
+    """Runs the oracle prover; returns the proof as a uint64 array."""
+    arr, ncols, logn, keep = tables_arg(traces)
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    cw = (C.c_uint32 * 7)(*cfg)
+    words = C.c_size_t()
+    ptr = lib.orc_prove_system(system_id, C.cast(arr, C.c_void_p), ncols, logn, rb, ra, userdata, len(userdata), cw, C.byref(words))
+    if not ptr:
+        raise RuntimeError(lib.orc_last_error().decode())
+    out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(words.value,)).copy()
+    lib.orc_free(ptr)
+    return out
+
+
+def verify_system(lib, system_id, proof: np.ndarray, cfg=STANDARD_FAST_CONFIG):
+    """Returns None if the oracle verifier accepts, else the rejection message."""
+    cw = (C.c_uint32 * 7)(*cfg)
+    proof = np.ascontiguousarray(proof, dtype=np.uint64)
+    rc = lib.orc_verify_system(system_id, u64ptr(proof), proof.size, cw)
+    return None if rc == 0 else lib.orc_last_error().decode()
 
 
 def u64ptr(a: np.ndarray):

@@ -5,6 +5,9 @@
 #include "poseidon.h"
 #include "fft.h"
 #include "plonky2_restated.h"
+#include "stark.h"
+#include "proof_io.h"
+#include "../zkm_b200/csrc/tables/systems.h"
 #include <cstring>
 #include <string>
 
@@ -112,6 +115,128 @@ void orc_batch_open(const void* h, uint32_t leaf, uint64_t* leaf_out, uint64_t* 
     MerkleProof p = b.merkle_tree.prove(leaf);
     for (size_t i = 0; i < p.siblings.size(); i++)
         for (int k = 0; k < 4; k++) siblings_out[i * 4 + k] = p.siblings[i].e[k].v;
+}
+
+
+// ---- STARK layer: prove / verify a System (oracle/stark.h) ----
+static StarkConfig make_cfg(const uint32_t* c) {
+    StarkConfig cfg;
+    if (c) {
+        cfg.fri.rate_bits = c[0]; cfg.fri.cap_height = c[1]; cfg.fri.proof_of_work_bits = c[2]; cfg.fri.num_query_rounds = c[3];
+        cfg.num_challenges = c[4]; cfg.fri.arity_bits = c[5]; cfg.fri.final_poly_bits = c[6];
+    }
+    return cfg;
+}
+// tables[t] = column pointers of table t (ncols[t] columns of 2^log_n[t] values).  Returns a malloc'ed
+// proof buffer (u64 words) or NULL (see orc_last_error).
+uint64_t* orc_prove_system(int system_id, const uint64_t* const* const* tables, const uint32_t* ncols, const uint32_t* log_n,
+                           const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                           const uint32_t* cfg_words, size_t* out_words) {
+    try {
+        System sys = zkm::tables::make_system(system_id);
+        StarkConfig cfg = make_cfg(cfg_words);
+        std::vector<Trace> traces(sys.kinds.size());
+        for (size_t t = 0; t < sys.kinds.size(); t++) {
+            size_t n = (size_t)1 << log_n[t];
+            traces[t].assign(ncols[t], std::vector<Fp>(n));
+            for (uint32_t c = 0; c < ncols[t]; c++)
+                for (size_t i = 0; i < n; i++) traces[t][c][i] = Fp(tables[t][c][i]);
+        }
+        PublicValues pv;
+        for (int i = 0; i < 8; i++) { pv.roots_before[i] = roots_before[i]; pv.roots_after[i] = roots_after[i]; }
+        pv.userdata.assign(userdata, userdata + userdata_len);
+        AllProof ap = prove_with_traces(sys, cfg, traces, pv);
+        std::vector<u64> w = serialize(ap);
+        uint64_t* out = (uint64_t*)malloc(w.size() * sizeof(u64));
+        memcpy(out, w.data(), w.size() * sizeof(u64));
+        *out_words = w.size();
+        return out;
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void orc_free(void* p) { free(p); }
+// 0 = accepted, -1 = rejected / malformed (orc_last_error says why).
+int orc_verify_system(int system_id, const uint64_t* proof, size_t words, const uint32_t* cfg_words) {
+    try {
+        System sys = zkm::tables::make_system(system_id);
+        StarkConfig cfg = make_cfg(cfg_words);
+        AllProof ap = deserialize(proof, words);
+        verify_proof(sys, ap, cfg);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// Constraint check on H (the reference's check_constraints, prover.rs:793-910, and the
+// generate => constraints-vanish tests): evaluates the table constraints of `kind` on every row of
+// the trace (next row cyclic) with alpha = 1-free accumulation per constraint; returns the number of
+// rows with a non-zero constraint, or -1 on error.  Transition constraints are skipped on the last row
+// and first/last-row constraints only apply there, as in the reference.
+long orc_check_table_constraints(int kind, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n) {
+    try {
+        size_t n = (size_t)1 << log_n;
+        if ((int)ncols != zkm::tables::table_num_columns(kind)) throw std::runtime_error("wrong column count");
+        std::atomic<long> bad(0);
+        Fp last = primitive_root_of_unity(log_n).inverse();
+        parallel_for(n, [&](size_t i) {
+            std::vector<Fp> lv(ncols), nv(ncols);
+            for (uint32_t c = 0; c < ncols; c++) { lv[c] = Fp(cols[c][i]); nv[c] = Fp(cols[c][(i + 1) % n]); }
+            Fp x = primitive_root_of_unity(log_n).pow(i);
+            // two random-ish alphas so that a cancelling combination is implausible
+            Consumer<Fp> yc({Fp(0x9E3779B97F4A7C15ULL % GL_P), Fp(0xC2B2AE3D27D4EB4FULL % GL_P)}, x - last,
+                            i == 0 ? Fp::one() : Fp::zero(), i == n - 1 ? Fp::one() : Fp::zero());
+            RowView<Fp> l{lv.data()}, nx{nv.data()};
+            if (!zkm::tables::eval_table<Fp, RowView<Fp>, Consumer<Fp>>(kind, l, nx, yc)) { bad = -(long)n - 1; return; }
+            if (!yc.accs[0].is_zero() || !yc.accs[1].is_zero()) bad++;
+        });
+        if (bad < 0) throw std::runtime_error("constraints of this table are not available");
+        return bad;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Poseidon table row generator (reference poseidon_stark.rs:51-95,105-145: poseidon_with_witness +
+// generate_trace_rows_for_perm): inputs[k*12..], timestamps[k] -> row-major rows[k*262..].  Test input
+// generator only.
+void orc_gen_poseidon_rows(const uint64_t* inputs, const uint64_t* timestamps, size_t count, uint64_t* rows) {
+    namespace pz = zkm::tables::poseidon;
+    parallel_for(count, [&](size_t k) {
+        uint64_t* row = rows + k * pz::NUM_COLUMNS;
+        for (int i = 0; i < pz::NUM_COLUMNS; i++) row[i] = 0;
+        row[pz::FILTER] = 1;
+        row[pz::TIMESTAMP] = timestamps[k];
+        PState s;
+        for (int i = 0; i < 12; i++) { s[i] = Fp(inputs[k * 12 + i]); row[pz::reg_in(i)] = s[i].v; }
+        int round = 0;
+        auto full = [&](int r, bool second) {
+            for (int i = 0; i < 12; i++) s[i] += Fp(POSEIDON_ALL_ROUND_CONSTANTS[12 * round + i]);
+            for (int i = 0; i < 12; i++) {
+                Fp x3 = s[i] * s[i] * s[i], x7 = x3 * x3 * s[i];
+                int base = second ? pz::reg_full1_s0(r, i) : pz::reg_full0_s0(r, i);
+                row[base] = x3.v; row[base + 1] = x7.v;
+                s[i] = x7;
+            }
+            mds_layer(s);
+            round++;
+        };
+        for (int r = 0; r < 4; r++) full(r, false);
+        for (int i = 0; i < 12; i++) s[i] += Fp(POSEIDON_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]);
+        {
+            PState o; o[0] = s[0];
+            for (int c = 0; c < 11; c++) { Fp acc; for (int r = 0; r < 11; r++) acc += s[r + 1] * Fp(POSEIDON_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r * 11 + c]); o[c + 1] = acc; }
+            s = o;
+        }
+        for (int r = 0; r < 22; r++) {
+            Fp x3 = s[0] * s[0] * s[0], x7 = x3 * x3 * s[0];
+            row[pz::reg_partial_s0(r)] = x3.v; row[pz::reg_partial_s0(r) + 1] = x7.v;
+            s[0] = x7;
+            if (r < 21) s[0] += Fp(POSEIDON_FAST_PARTIAL_ROUND_CONSTANTS[r]);
+            Fp d = s[0] * Fp(POSEIDON_MDS_CIRC[0] + POSEIDON_MDS_DIAG[0]);
+            for (int j = 1; j < 12; j++) d += s[j] * Fp(POSEIDON_FAST_PARTIAL_ROUND_W_HATS[r * 11 + j - 1]);
+            PState o; o[0] = d;
+            for (int j = 1; j < 12; j++) o[j] = s[j] + s[0] * Fp(POSEIDON_FAST_PARTIAL_ROUND_VS[r * 11 + j - 1]);
+            s = o;
+        }
+        round += 22;
+        for (int r = 0; r < 4; r++) full(r, true);
+        for (int i = 0; i < 12; i++) row[pz::reg_out(i)] = s[i].v;
+    });
 }
 
 }  // extern "C"

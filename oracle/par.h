@@ -9,6 +9,8 @@
 #include <functional>
 #include <cstdlib>
 #include <algorithm>
+#include <exception>
+#include <mutex>
 
 namespace orc {
 
@@ -33,12 +35,20 @@ inline void parallel_for(size_t n, F&& f, size_t chunk = 0) {
     }
     if (chunk == 0) chunk = std::max<size_t>(1, n / ((size_t)nt * 8));
     std::atomic<size_t> next(0);
+    std::exception_ptr err;
+    std::mutex err_mu;
     auto worker = [&] {
-        for (;;) {
-            size_t b = next.fetch_add(chunk);
-            if (b >= n) break;
-            size_t e = std::min(n, b + chunk);
-            for (size_t i = b; i < e; i++) f(i);
+        try {
+            for (;;) {
+                size_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                size_t e = std::min(n, b + chunk);
+                for (size_t i = b; i < e; i++) f(i);
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (!err) err = std::current_exception();
+            next.store(n);
         }
     };
     std::vector<std::thread> ts;
@@ -46,6 +56,7 @@ inline void parallel_for(size_t n, F&& f, size_t chunk = 0) {
     for (int t = 1; t < spawn; t++) ts.emplace_back(worker);
     worker();
     for (auto& t : ts) t.join();
+    if (err) std::rethrow_exception(err);
 }
 
 }  // namespace orc

@@ -1,0 +1,66 @@
+// The Systems the library can prove.  SYSTEM_ALL_STARK is the reference's AllStark (all_stark.rs);
+// the others are small self-contained Systems (same code path, fewer tables) whose valid traces can
+// be generated without the MIPS emulator, used for end-to-end prove -> verify parity tests in the
+// spirit of the reference's single-table prove tests (poseidon_stark.rs:751-816, keccak_stark.rs:689-754).
+#pragma once
+#include "registry.h"
+
+namespace zkm {
+namespace tables {
+
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4 };
+
+// A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
+inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
+    CrossTableLookup c;
+    c.looking_tables.push_back(TableWithColumns(table, cols, f));
+    c.looked_table = TableWithColumns(table, cols, f);
+    return c;
+}
+
+inline System make_system(int id) {
+    System s;
+    switch (id) {
+        case SYSTEM_LOGIC:
+            s.kinds = {T_LOGIC};
+            s.ctls.push_back(self_ctl(0, logic::ctl_data(), logic::ctl_filter()));
+            return s;
+        case SYSTEM_POSEIDON:
+            s.kinds = {T_POSEIDON};
+            s.ctls.push_back(self_ctl(0, poseidon::ctl_data_inputs(), poseidon::ctl_filter_inputs()));
+            s.ctls.push_back(self_ctl(0, poseidon::ctl_data_outputs(), poseidon::ctl_filter_outputs()));
+            return s;
+        case SYSTEM_MEMORY:
+            s.kinds = {T_MEMORY};
+            s.ctls.push_back(self_ctl(0, memory::ctl_data(), memory::ctl_filter()));
+            return s;
+        case SYSTEM_MINI3: {
+            // tables: 0 = Poseidon, 1 = Logic, 2 = Memory
+            s.kinds = {T_POSEIDON, T_LOGIC, T_MEMORY};
+            // Logic looked by three looking sets of the same table (-> 2 helper columns): rows with
+            // IS_AND, rows with IS_OR, rows with IS_XOR + IS_NOR; their union is the looked filter.
+            CrossTableLookup a;
+            a.looking_tables.push_back(TableWithColumns(1, logic::ctl_data(), Filter::new_simple(Column::single(logic::IS_AND))));
+            a.looking_tables.push_back(TableWithColumns(1, logic::ctl_data(), Filter::new_simple(Column::single(logic::IS_OR))));
+            a.looking_tables.push_back(TableWithColumns(1, logic::ctl_data(), Filter::new_simple(Column::sum({logic::IS_XOR, logic::IS_NOR}))));
+            a.looked_table = TableWithColumns(1, logic::ctl_data(), logic::ctl_filter());
+            s.ctls.push_back(a);
+            s.ctls.push_back(self_ctl(0, poseidon::ctl_data_inputs(), poseidon::ctl_filter_inputs()));
+            s.ctls.push_back(self_ctl(0, poseidon::ctl_data_outputs(), poseidon::ctl_filter_outputs()));
+            // Memory looked by two looking sets of itself (reads, writes)
+            CrossTableLookup m;
+            m.looking_tables.push_back(TableWithColumns(2, memory::ctl_data(), Filter::new_(
+                {{Column::single(memory::FILTER), Column::single(memory::IS_READ)}}, {})));
+            m.looking_tables.push_back(TableWithColumns(2, memory::ctl_data(), Filter::new_(
+                {{Column::single(memory::FILTER), Column::linear_combination_with_constant({{memory::IS_READ, FP - 1}}, 1)}}, {})));
+            m.looked_table = TableWithColumns(2, memory::ctl_data(), memory::ctl_filter());
+            s.ctls.push_back(m);
+            return s;
+        }
+        default:
+            throw std::runtime_error("unknown or not yet available system id");
+    }
+}
+
+}  // namespace tables
+}  // namespace zkm

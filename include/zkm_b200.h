@@ -71,6 +71,48 @@ int zkm_b200_profile_reset(char** err);
 int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, double* bytes, char** err);
 char* zkm_b200_profile_families(void);
 
+/* ---- the prover --------------------------------------------------------------------------------
+ *
+ * zkm_b200_prove_with_traces replaces reference prover/src/prover.rs:130-140
+ *   prove_with_traces(all_stark, config, trace_poly_values: [Vec<PolynomialValues<F>>; NUM_TABLES],
+ *                     public_values, timing) -> Result<AllProof<F, C, D>>
+ * for F = GoldilocksField, C = PoseidonGoldilocksConfig, D = 2.  tables[] is indexed by the `Table`
+ * enum (all_stark.rs:97-110); roots_before/roots_after/userdata are PublicValues (proof.rs:52-61).
+ * Errors the reference raises as panics/ensure! come back as -1 with the same message text
+ * ("FRI total reduction arity is too large.", "No CTL?", "Opening point is in the subgroup.",
+ * "Non-binary filter?").
+ *
+ * Proof buffer layout (u64 words, little endian; extension element = 2 words, digest = 4 words,
+ * "vec X" = length word then the items):
+ *   magic "ZKMPROOF", version 1, num_tables,
+ *   num_challenges, (beta, gamma) x num_challenges               -- AllProof.ctl_challenges
+ *   roots_before[8], roots_after[8], vec userdata bytes           -- AllProof.public_values
+ *   per table (StarkProofWithMetadata, proof.rs:178-201):
+ *     init_challenger_state[12]
+ *     vec digest trace_cap, vec digest auxiliary_polys_cap, vec digest quotient_polys_cap
+ *     vec ext local_values, vec ext next_values, vec ext auxiliary_polys, vec ext auxiliary_polys_next,
+ *     vec F ctl_zs_first, vec ext quotient_polys                  -- StarkOpeningSet (proof.rs:283-296)
+ *     FriProof: vec (vec digest) commit_phase_merkle_caps,
+ *               vec query_round { vec oracle { vec F leaf row, vec digest siblings },
+ *                                 vec step   { vec ext evals,  vec digest siblings } },
+ *               vec ext final_poly, pow_witness
+ * The buffer is malloc'ed by the library and released with zkm_b200_free. */
+int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t roots_before[8], const uint32_t roots_after[8],
+                               const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
+                               uint64_t** proof_out, size_t* proof_words, char** err);
+/* Same prover over another System of tables (zkm_b200/csrc/tables/systems.h: 0 = AllStark, 1 = Logic,
+ * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory): small Systems whose valid traces can be
+ * generated without the MIPS emulator, for prove -> verify parity tests. */
+int zkm_b200_prove_system(int system_id, const zkm_table_t* tables, uint32_t num_tables, const uint32_t* roots_before,
+                          const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                          const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err);
+/* As above with the trace columns already resident in device memory: d_tables[t] is a device pointer to
+ * shapes[t].ncols * 2^log_n u64, column-major (shapes[t].cols is ignored).  bench.py's `value` metric. */
+int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const uint64_t* const* d_tables, uint32_t num_tables,
+                                 const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata,
+                                 uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
+                                 char** err);
+
 /* ---- staged API (stage-by-stage parity against the oracle) ------------------------------- */
 
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height) — prover.rs:154-163,

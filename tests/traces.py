@@ -37,8 +37,7 @@ def memory_trace(log_n: int, seed: int = 2, used_frac: float = 0.7) -> np.ndarra
     ctx = rng.integers(0, 3, size=used)
     seg = rng.integers(0, 4, size=used)
     virt = rng.integers(0, max(2, n // 16), size=used)
-    ts = np.sort(rng.integers(1, max(3, n // 2), size=used))
-    ts = ts + np.arange(used)                      # strictly increasing timestamps
+    ts = 1 + rng.permutation(used)                 # distinct timestamps below n: every delta is range-checkable
     order = np.lexsort((ts, virt, seg, ctx))
     ctx, seg, virt, ts = ctx[order], seg[order], virt[order], ts[order]
     is_read = rng.integers(0, 2, size=used)

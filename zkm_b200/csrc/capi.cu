@@ -3,6 +3,8 @@
 #include "../../include/zkm_b200.h"
 #include "batch.cuh"
 #include "poseidon.cuh"
+#include "prover.cuh"
+#include "tables/systems.h"
 #include <cstring>
 #include <cstdlib>
 
@@ -142,6 +144,64 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
     } catch (...) { delete h; throw; }
     if (cap_out) memcpy(cap_out, h->b.tree.cap.data(), h->b.tree.cap.size() * sizeof(u64));
     *out = h;
+    ZKM_API_END
+}
+
+static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_tables, const uint64_t* const* d_tables,
+                        const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                        const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words) {
+    Ctx& c = ctx();
+    ZKM_CHECK(tables && roots_before && roots_after && cfg && proof_out && proof_words, "null argument");
+    ZKM_CHECK(userdata || userdata_len == 0, "null userdata");
+    StarkCfg sc;
+    sc.rate_bits = cfg->rate_bits; sc.cap_height = cfg->cap_height; sc.pow_bits = cfg->pow_bits; sc.num_queries = cfg->num_queries;
+    sc.num_challenges = cfg->num_challenges; sc.arity_bits = cfg->arity_bits; sc.final_poly_bits = cfg->final_poly_bits;
+    std::vector<TableInput> in(num_tables);
+    for (uint32_t t = 0; t < num_tables; t++) {
+        in[t].ncols = tables[t].ncols; in[t].log_n = tables[t].log_n;
+        ZKM_CHECK(tables[t].log_n <= 26, "trace too long");
+        size_t n = (size_t)1 << tables[t].log_n;
+        if (d_tables) {
+            ZKM_CHECK(d_tables[t] != nullptr, "null device table");
+            in[t].values.alloc((size_t)tables[t].ncols * n, c.stream);
+            ZKM_CUDA(cudaMemcpyAsync(in[t].values.p, d_tables[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream));
+        } else {
+            in[t].values = upload_table(&tables[t]);
+        }
+    }
+    PublicInputs pv;
+    for (int i = 0; i < 8; i++) { pv.roots_before[i] = roots_before[i]; pv.roots_after[i] = roots_after[i]; }
+    pv.userdata.assign(userdata, userdata + userdata_len);
+    std::vector<u64> w = prove_system(system_id, sc, in, pv);
+    uint64_t* out = (uint64_t*)malloc(w.size() * sizeof(u64));
+    ZKM_CHECK(out, "out of host memory");
+    memcpy(out, w.data(), w.size() * sizeof(u64));
+    *proof_out = out; *proof_words = w.size();
+    return 0;
+}
+
+int zkm_b200_prove_system(int system_id, const zkm_table_t* tables, uint32_t num_tables, const uint32_t* roots_before,
+                          const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
+                          uint64_t** proof_out, size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    prove_common(system_id, tables, num_tables, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
+    ZKM_API_END
+}
+
+int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const uint64_t* const* d_tables, uint32_t num_tables,
+                                 const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                                 const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(d_tables, "null device tables");
+    prove_common(system_id, shapes, num_tables, d_tables, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
+    ZKM_API_END
+}
+
+int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t roots_before[8], const uint32_t roots_after[8],
+                               const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out,
+                               size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
     ZKM_API_END
 }
 

@@ -101,6 +101,7 @@ struct gl2 {
     static ZKM_HD gl2 zero() { return gl2(); }
     static ZKM_HD gl2 one() { return gl2(gl::one(), gl()); }
 };
+ZKM_HD gl2 mk2(u64 a, u64 b) { return gl2(gl(a), gl(b)); }
 ZKM_HD gl2 operator+(gl2 x, gl2 y) { return gl2(x.a + y.a, x.b + y.b); }
 ZKM_HD gl2 operator-(gl2 x, gl2 y) { return gl2(x.a - y.a, x.b - y.b); }
 ZKM_HD gl2 operator-(gl2 x) { return gl2(-x.a, -x.b); }

@@ -143,8 +143,8 @@ struct NttTables::Impl {
     std::map<std::pair<int, int>, std::shared_ptr<PowTableOwner>> roots;
     // small per-radix twiddle arrays  w_R^k k<R/2
     std::map<std::pair<int, int>, std::shared_ptr<DevBuf>> tw;
-    // coset shift tables: key (log_n, rate_bits, j, inverse)
-    std::map<std::tuple<int, int, int, int>, std::shared_ptr<PowTableOwner>> shifts;
+    // coset shift tables: key (log_n, rate_bits, j, inverse, shift_exp_bits)
+    std::map<std::tuple<int, int, int, int, int>, std::shared_ptr<PowTableOwner>> shifts;
 };
 NttTables::NttTables() : impl(new Impl) {}
 NttTables::~NttTables() { delete impl; }
@@ -178,12 +178,13 @@ static const u64* get_tw(NttTables& T, int log_r, int inverse, cudaStream_t s) {
     return b->p;
 }
 // powers of shift^(+-1) where shift = base * w_{n*2^rate_bits}^j
-static std::shared_ptr<PowTableOwner> get_shift(NttTables& T, int log_n, int rate_bits, int j, int inverse, cudaStream_t s) {
+static std::shared_ptr<PowTableOwner> get_shift(NttTables& T, int log_n, int rate_bits, int j, int inverse, cudaStream_t s,
+                                                int shift_exp_bits = 0) {
     std::lock_guard<std::mutex> g(T.impl->mu);
-    auto key = std::make_tuple(log_n, rate_bits, j, inverse);
+    auto key = std::make_tuple(log_n, rate_bits, j, inverse, shift_exp_bits);
     auto it = T.impl->shifts.find(key);
     if (it != T.impl->shifts.end()) return it->second;
-    gl sh = gl(GL_GENERATOR) * gl_pow(gl_root_of_unity(log_n + rate_bits), (u64)j);
+    gl sh = gl_exp2(gl(GL_GENERATOR), shift_exp_bits) * gl_pow(gl_root_of_unity(log_n + rate_bits), (u64)j);
     if (inverse) sh = gl_inv(sh);
     auto t = make_pow_table(sh, log_n, s);
     T.impl->shifts[key] = t;
@@ -268,12 +269,12 @@ void ntt_inverse(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out
     ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 1, nullptr, ninv.v, s);
 }
 void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t out_cs, int ncols, int log_n, int rate_bits,
-               cudaStream_t s) {
+               cudaStream_t s, int shift_exp_bits) {
     ZKM_CHECK(rate_bits <= 2, "rate_bits > 2 unsupported");
     int nz = 1 << rate_bits;
     PowTable pre[4];
     std::shared_ptr<PowTableOwner> keep[4];
-    for (int j = 0; j < nz; j++) { keep[j] = get_shift(t, log_n, rate_bits, j, 0, s); pre[j] = keep[j]->view; }
+    for (int j = 0; j < nz; j++) { keep[j] = get_shift(t, log_n, rate_bits, j, 0, s, shift_exp_bits); pre[j] = keep[j]->view; }
     ntt_generic(t, coeffs, in_cs, 0, lde, out_cs, (size_t)1 << log_n, ncols, nz, log_n, 0, pre, 1, s);
 }
 

@@ -1,0 +1,212 @@
+// Quotient (constraint) evaluation on the degree-2n coset: one thread per point.
+// Replaces reference compute_quotient_polys (prover/src/prover.rs:645-789) + eval_vanishing_poly
+// (vanishing_poly.rs:17-46): table constraints (tables/*.h templates, the analogue of each table's
+// eval_packed_generic), logUp checks (lookup.rs:138-198) and CTL checks (cross_table_lookup.rs:
+// 1006-1150), folded with the alphas in emission order (constraint_consumer.rs:52-75), then
+// multiplied by 1/Z_H(x) (ZeroPolyOnCoset, 2 distinct values).
+//
+// Data layout: the trace / auxiliary LDEs are column-major and coset-major (ntt.cuh): LDE natural index
+// m = 4*idx + j sits at j*n + idx.  The quotient domain is the even natural indices, i.e. cosets
+// j = 0 and j = 2, and the "next" row (m + 4) is idx + 1 of the same coset: every column read is a
+// fully coalesced 8-byte-per-lane access and the next-row read hits the neighbouring lane's line.
+// Only half of the LDE (2 of 4 cosets) is read: 16*n*(C+A) algorithmic bytes.
+#include "aux.cuh"
+#include "tables/registry.h"
+
+namespace zkm {
+
+struct LdeRow {
+    const u64* base; size_t stride;
+    __device__ __forceinline__ gl operator[](int c) const { return gl(__ldg(base + (size_t)c * stride)); }
+};
+
+struct DevConsumer {
+    gl alpha[MAX_CHALLENGES], acc[MAX_CHALLENGES];
+    int na;
+    gl z_last, l_first, l_last;
+    __device__ __forceinline__ void constraint(gl c) {
+#pragma unroll
+        for (int a = 0; a < MAX_CHALLENGES; a++) if (a < na) acc[a] = acc[a] * alpha[a] + c;
+    }
+    __device__ __forceinline__ void constraint_transition(gl c) { constraint(c * z_last); }
+    __device__ __forceinline__ void constraint_first_row(gl c) { constraint(c * l_first); }
+    __device__ __forceinline__ void constraint_last_row(gl c) { constraint(c * l_last); }
+};
+
+struct QParams {
+    const u64* tr; size_t tr_cs;
+    const u64* ax; size_t ax_cs;
+    int log_n, na;
+    u64 alphas[MAX_CHALLENGES];
+    AuxChallenges ch;
+    DProgramView prog;
+    PowTable w2n;                 // powers of w_{2n}
+    u64 zh[2], zh_inv[2];         // Z_H(x_i) for i even / odd, and inverses
+    u64 last, g, n_inv;           // g^(n-1) = g^-1, g = w_n, 1/n
+    u64* q;
+};
+
+// Column::eval (no next-row terms), used by the logUp Z check (lookup.rs:182-187).
+__device__ __forceinline__ gl dcol_eval_local(const DProgramView& P, int ci, const LdeRow& lv) {
+    const DColumn c = P.cols[ci];
+    gl r(c.constant);
+    for (int k = 0; k < c.lin_cnt; k++) { DTerm t = P.terms[c.lin_off + k]; r = r + lv[t.col] * gl(t.coef); }
+    return r;
+}
+
+// eval_helper_columns (cross_table_lookup.rs:1006-1057) for parts [part_off, part_off + part_cnt).
+__device__ __forceinline__ void dev_eval_helper_columns(const DProgramView& P, int part_off, int part_cnt, int num_helpers, const LdeRow& lv,
+                                                        const LdeRow& nv, const LdeRow& al, int helper_aux, gl beta, gl gamma, DevConsumer& yc) {
+    if (num_helpers == 0) return;
+    for (int j = 0; 2 * j < part_cnt; j++) {
+        gl h = al[helper_aux + j];
+        const DPart p0 = P.parts[part_off + 2 * j];
+        gl c0 = dpart_combine(P, p0, lv, nv, beta, gamma);
+        gl f0 = dfilter_eval(P, p0.filter, lv, nv);
+        if (2 * j + 1 < part_cnt) {
+            const DPart p1 = P.parts[part_off + 2 * j + 1];
+            gl c1 = dpart_combine(P, p1, lv, nv, beta, gamma);
+            gl f1 = dfilter_eval(P, p1.filter, lv, nv);
+            yc.constraint(c1 * c0 * h - f0 * c1 - f1 * c0);
+        } else {
+            yc.constraint(c0 * h - f0);
+        }
+    }
+}
+
+__device__ __forceinline__ void dev_eval_lookups(const QParams& q, const LdeRow& lv, const LdeRow& nv, const LdeRow& al, const LdeRow& an,
+                                                 DevConsumer& yc) {
+    const DProgramView& P = q.prog;
+    for (int li = 0; li < P.num_lookups; li++) {
+        const DLookup l = P.lookups[li];
+        gl challenge(q.ch.beta[l.challenge]);
+        dev_eval_helper_columns(P, l.part_off, l.part_cnt, l.num_helpers, lv, nv, al, l.aux_start, gl::one(), challenge, yc);
+        gl z = al[l.aux_start + l.num_helpers], next_z = an[l.aux_start + l.num_helpers];
+        gl twc = dcol_eval_local(P, l.table_col, lv) + challenge;
+        gl hs = gl::zero();
+        for (int j = 0; j < l.num_helpers; j++) hs = hs + al[l.aux_start + j];
+        gl y = hs * twc - dcol_eval_local(P, l.freq_col, lv);
+        yc.constraint_first_row(z);
+        yc.constraint((next_z - z) * twc - y);
+    }
+}
+
+__device__ __forceinline__ void dev_eval_ctl_checks(const QParams& q, const LdeRow& lv, const LdeRow& nv, const LdeRow& al, const LdeRow& an,
+                                                    DevConsumer& yc) {
+    const DProgramView& P = q.prog;
+    for (int zi = 0; zi < P.num_zs; zi++) {
+        const DZ z = P.zs[zi];
+        gl beta(q.ch.beta[z.challenge]), gamma(q.ch.gamma[z.challenge]);
+        dev_eval_helper_columns(P, z.part_off, z.part_cnt, z.num_helpers, lv, nv, al, z.helper_aux, beta, gamma, yc);
+        gl local_z = al[z.z_aux], next_z = an[z.z_aux];
+        if (z.num_helpers) {
+            gl hs = gl::zero();
+            for (int j = 0; j < z.num_helpers; j++) hs = hs + al[z.helper_aux + j];
+            yc.constraint_last_row(local_z - hs);
+            yc.constraint_transition(local_z - next_z - hs);
+        } else if (z.part_cnt > 1) {
+            const DPart p0 = P.parts[z.part_off], p1 = P.parts[z.part_off + 1];
+            gl c0 = dpart_combine(P, p0, lv, nv, beta, gamma), c1 = dpart_combine(P, p1, lv, nv, beta, gamma);
+            gl f0 = dfilter_eval(P, p0.filter, lv, nv), f1 = dfilter_eval(P, p1.filter, lv, nv);
+            yc.constraint_last_row(c0 * c1 * local_z - f0 * c1 - f1 * c0);
+            yc.constraint_transition(c0 * c1 * (local_z - next_z) - f0 * c1 - f1 * c0);
+        } else {
+            const DPart p0 = P.parts[z.part_off];
+            gl c0 = dpart_combine(P, p0, lv, nv, beta, gamma);
+            gl f0 = dfilter_eval(P, p0.filter, lv, nv);
+            yc.constraint_last_row(c0 * local_z - f0);
+            yc.constraint_transition(c0 * (local_z - next_z) - f0);
+        }
+    }
+}
+
+__device__ __forceinline__ gl gl_inv_q(gl x) {
+    gl x2 = x * x * x;
+    gl x4 = gl_exp2(x2, 2) * x2;
+    gl x8 = gl_exp2(x4, 4) * x4;
+    gl x16 = gl_exp2(x8, 8) * x8;
+    gl x32 = gl_exp2(x16, 16) * x16;
+    gl x31 = gl_exp2(x16, 8) * x8;
+    x31 = gl_exp2(x31, 4) * x4;
+    x31 = gl_exp2(x31, 2) * x2;
+    x31 = gl_exp2(x31, 1) * x;
+    return gl_exp2(x31, 33) * x32;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) quotient_kernel(QParams q) {
+    const size_t n = (size_t)1 << q.log_n;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    const size_t half = t >> q.log_n, idx = t & (n - 1);
+    const size_t i = 2 * idx + half;                        // index in the quotient domain 7*H_{2n}
+    const size_t pos = (2 * half) * n + idx, pos_next = (2 * half) * n + ((idx + 1) & (n - 1));
+    LdeRow lv{q.tr + pos, q.tr_cs}, nv{q.tr + pos_next, q.tr_cs};
+    LdeRow al{q.ax + pos, q.ax_cs}, an{q.ax + pos_next, q.ax_cs};
+
+    gl x = gl(GL_GENERATOR) * pow_lookup(q.w2n, i);
+    DevConsumer yc;
+    yc.na = q.na;
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++) { yc.alpha[a] = gl(q.alphas[a]); yc.acc[a] = gl::zero(); }
+    yc.z_last = x - gl(q.last);
+    // L_first(x) = (x^n - 1) / (n (x - 1)),  L_last(x) = (x^n - 1) / (n (g x - 1))   (verifier.rs:347-354;
+    // the reference prover tabulates the same two polynomials with an LDE of the selectors, prover.rs:677-681)
+    gl d0 = x - gl::one(), d1 = gl(q.g) * x - gl::one();
+    gl inv = gl_inv_q(d0 * d1);
+    gl zhx = gl(q.zh[i & 1]) * gl(q.n_inv);
+    yc.l_first = zhx * (inv * d1);
+    yc.l_last = zhx * (inv * d0);
+
+    tables::eval_table<gl, LdeRow, DevConsumer>(KIND, lv, nv, yc);
+    if (q.prog.num_lookups) dev_eval_lookups(q, lv, nv, al, an, yc);
+    dev_eval_ctl_checks(q, lv, nv, al, an, yc);
+
+    gl zi(q.zh_inv[i & 1]);
+#pragma unroll
+    for (int a = 0; a < MAX_CHALLENGES; a++)
+        if (a < q.na) q.q[(size_t)a * 2 * n + i] = (yc.acc[a] * zi).v;
+}
+
+typedef void (*quotient_kernel_t)(QParams);
+static quotient_kernel_t quotient_kernel_for(int kind) {
+    switch (kind) {
+        case tables::T_POSEIDON: return quotient_kernel<tables::T_POSEIDON>;
+        case tables::T_LOGIC: return quotient_kernel<tables::T_LOGIC>;
+        case tables::T_MEMORY: return quotient_kernel<tables::T_MEMORY>;
+        default:
+            throw std::runtime_error(std::string("constraints of table ") + tables::table_name(kind) + " are not available on the device");
+    }
+}
+
+void compute_quotient_values(int kind, const DProgram& prog, const tables::TableLayout& L, const Batch& trace, const Batch& aux,
+                             const AuxChallenges& ch, const u64* alphas, int num_alphas, u64* d_q, cudaStream_t s) {
+    ZKM_CHECK(num_alphas <= MAX_CHALLENGES, "too many challenges");
+    ZKM_CHECK(trace.rate_bits == 2 && aux.rate_bits == 2, "quotient kernel expects rate_bits = 2");
+    ZKM_CHECK(trace.log_n == aux.log_n && trace.ncols == L.ncols && aux.ncols == L.num_aux(), "quotient: batch shape mismatch");
+    int log_n = trace.log_n;
+    size_t n = (size_t)1 << log_n;
+    QParams q = {};
+    q.tr = trace.lde.p; q.tr_cs = trace.lde_n();
+    q.ax = aux.lde.p; q.ax_cs = aux.lde_n();
+    q.log_n = log_n; q.na = num_alphas;
+    for (int a = 0; a < num_alphas; a++) q.alphas[a] = alphas[a];
+    q.ch = ch;
+    q.prog = prog.view;
+    auto tab = make_pow_table(gl_root_of_unity(log_n + 1), log_n + 1, s);
+    q.w2n = tab->view;
+    gl gn = gl_exp2(gl(GL_GENERATOR), log_n);                 // 7^n
+    gl z0 = gn - gl::one(), z1 = -gn - gl::one();              // x^n = 7^n * (-1)^i
+    q.zh[0] = z0.v; q.zh[1] = z1.v;
+    q.zh_inv[0] = gl_inv(z0).v; q.zh_inv[1] = gl_inv(z1).v;
+    gl g = gl_root_of_unity(log_n);
+    q.g = g.v; q.last = gl_inv(g).v; q.n_inv = gl_inv(gl((u64)n)).v;
+    q.q = d_q;
+    quotient_kernel_t k = quotient_kernel_for(kind);
+    ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
+    k<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(q);
+    ZKM_LAUNCHED();
+    ZKM_CUDA(cudaStreamSynchronize(s));                      // keeps `tab` alive until the kernel has run
+}
+
+}  // namespace zkm

@@ -31,7 +31,7 @@ EXPORTS = [
     "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute",
-    "zkm_b200_synth_columns_device", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 
@@ -63,6 +63,15 @@ def load():
     lib.zkm_b200_ntt.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     lib.zkm_b200_poseidon_permute.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkm_b200_synth_columns_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
+    u32p = C.POINTER(C.c_uint32)
+    lib.zkm_b200_prove_with_traces.argtypes = [C.POINTER(Table), u32p, u32p, C.c_char_p, C.c_uint32, C.POINTER(StarkConfig),
+                                               C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_prove_system.argtypes = [C.c_int, C.POINTER(Table), C.c_uint32, u32p, u32p, C.c_char_p, C.c_uint32,
+                                          C.POINTER(StarkConfig), C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_prove_system_device.argtypes = [C.c_int, C.POINTER(Table), C.POINTER(C.c_void_p), C.c_uint32, u32p, u32p, C.c_char_p,
+                                                 C.c_uint32, C.POINTER(StarkConfig), C.POINTER(u64p), C.POINTER(C.c_size_t),
+                                                 C.POINTER(C.c_void_p)]
+    lib.zkm_b200_free.argtypes = [C.c_void_p]
     lib.zkm_b200_timer_start.argtypes = [C.POINTER(C.c_void_p)]
     lib.zkm_b200_timer_stop.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
     lib.zkm_b200_profile_enable.argtypes = [C.c_int]
@@ -113,3 +122,29 @@ def init(device: int = 0):
         check(lib, lib.zkm_b200_init(device, C.byref(err)), err)
         _inited = True
     return lib
+
+
+def standard_fast_config(lib=None):
+    lib = lib or load()
+    c = StarkConfig()
+    lib.zkm_b200_standard_fast_config(C.byref(c))
+    return c
+
+
+def prove_system(lib, system_id, traces, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):
+    """traces: list of (ncols, n) uint64 arrays (host).  Returns the proof buffer as a uint64 array."""
+    cfg = cfg or standard_fast_config(lib)
+    T = len(traces)
+    made = [make_table(np.ascontiguousarray(t)) for t in traces]
+    arr = (Table * T)(*[m[0] for m in made])
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    out = C.POINTER(C.c_uint64)()
+    words = C.c_size_t()
+    err = C.c_void_p()
+    rc = lib.zkm_b200_prove_system(system_id, arr, T, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words),
+                                   C.byref(err))
+    check(lib, rc, err)
+    proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+    lib.zkm_b200_free(out)
+    return proof

@@ -130,6 +130,13 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
 /* Fills a device buffer (ncols x 2^log_n u64, column-major) with the synthetic SplitMix64 columns of
  * BASELINE.md §3 (stream seed | column index, value mod p).  Benchmark input generator. */
 int zkm_b200_synth_columns_device(uint64_t* d_out, uint32_t ncols, uint32_t log_n, uint64_t seed, char** err);
+/* Synthetic trace of table `table` of System `system_id`: uniform cells, with the columns
+ * read by CTL filters drawn so that every filter is 0/1.  _device writes ncols*2^log_n u64 (column-major)
+ * to a device pointer, the other variant to a host buffer.  Benchmark / parity input generator. */
+int zkm_b200_synth_trace_device(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, uint64_t* d_out, char** err);
+int zkm_b200_synth_trace(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, uint64_t* host_out, char** err);
+/* Number of tables of a System and the column count of each (AllStark: 12 tables). */
+int zkm_b200_system_shape(int system_id, uint32_t* num_tables, uint32_t* ncols_out, uint32_t max_tables, char** err);
 void zkm_b200_batch_free(zkm_batch_t* b);
 /* Coefficients of polynomial `col` (2^log_n u64). */
 int zkm_b200_batch_get_coeffs(const zkm_batch_t* b, uint32_t col, uint64_t* out, char** err);

@@ -83,3 +83,16 @@ def test_gpu_wrong_shape_errors(zkm):
         zl.prove_system(zkm, tr.SYSTEM_LOGIC, [np.zeros((5, 64), dtype=np.uint64)])
     with pytest.raises(zl.ZkmError, match="wrong number of tables"):
         zl.prove_system(zkm, tr.SYSTEM_MINI3, [tr.logic_trace(6)])
+
+
+def test_all_stark_synthetic_proof_equals_oracle(zkm, orc):
+    """The full 12-table AllStark (all_stark.rs) on synthetic traces at small heights:
+    every table's constraint evaluator, the 15 CTLs and the Arithmetic/Memory logUp lookups run on the
+    device and the proof must equal the oracle's word for word.  (Synthetic traces are not valid
+    executions, so the proof is not expected to verify.)"""
+    heights = [16, 7, 6, 6, 6, 6, 6, 7, 6, 6, 8, 9]
+    traces = zl.synth_traces(zkm, tr.SYSTEM_ALL_STARK, heights)
+    assert [t.shape[0] for t in traces] == [54, 259, 262, 110, 2431, 470, 78, 76, 224, 127, 69, 13]
+    gpu = zl.prove_system(zkm, tr.SYSTEM_ALL_STARK, traces)
+    cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
+    assert _first_diff(gpu, cpu) is None

@@ -7,6 +7,7 @@
 #include "tables/systems.h"
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 
 using namespace zkm;
 
@@ -283,6 +284,85 @@ int zkm_b200_synth_columns_device(uint64_t* d_out, uint32_t ncols, uint32_t log_
     synth_columns_kernel<<<grid, 256, 0, c.stream>>>(d_out, n, seed);
     ZKM_LAUNCHED();
     ZKM_CUDA(cudaStreamSynchronize(c.stream));
+    ZKM_API_END
+}
+
+// Synthetic segment traces: every cell uniform SplitMix64 mod p, except the columns read
+// by CTL filters, which are drawn so that every Filter evaluates to 0 or 1 (at most one flag set per row,
+// with probability 1/2), because get_helper_cols rejects non-binary filters (cross_table_lookup.rs:741).
+// Such traces are not valid executions: the prover runs to completion, the proof does not verify.
+__global__ void synth_flags_kernel(u64* out, size_t n, const int* flag_cols, int nflags, u64 seed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 z = (seed ^ 0xF1A6F1A6F1A6F1A6ULL) + (u64)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    int hot = (z & 1) ? (int)((z >> 1) % (u64)nflags) : -1;
+    for (int k = 0; k < nflags; k++) out[(size_t)flag_cols[k] * n + i] = (k == hot) ? 1 : 0;
+}
+
+static std::vector<int> filter_columns_of_table(const tables::System& sys, int t) {
+    std::vector<int> cols;
+    auto add_col = [&](const tables::Column& c) {
+        for (auto& p : c.lin) cols.push_back(p.first);
+        for (auto& p : c.next) cols.push_back(p.first);
+    };
+    auto add_filter = [&](const tables::Filter& f) {
+        for (auto& pr : f.products) { add_col(pr.first); add_col(pr.second); }
+        for (auto& c : f.constants) add_col(c);
+    };
+    for (auto& ctl : sys.ctls) {
+        for (auto& lt : ctl.looking_tables) if (lt.table == t) add_filter(lt.filter);
+        if (ctl.looked_table.table == t) add_filter(ctl.looked_table.filter);
+    }
+    for (auto& lk : tables::table_lookups(sys.kinds[t])) for (auto& f : lk.filter_columns) add_filter(f);
+    std::sort(cols.begin(), cols.end());
+    cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    return cols;
+}
+
+static void synth_trace_dev(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, u64* d_out) {
+    Ctx& c = ctx();
+    tables::System sys = tables::make_system(system_id);
+    ZKM_CHECK(table < sys.kinds.size(), "table index out of range");
+    int ncols = tables::table_num_columns(sys.kinds[table]);
+    size_t n = (size_t)1 << log_n;
+    dim3 grid((unsigned)((n + 255) / 256), ncols);
+    synth_columns_kernel<<<grid, 256, 0, c.stream>>>(d_out, n, seed);
+    ZKM_LAUNCHED();
+    std::vector<int> flags = filter_columns_of_table(sys, (int)table);
+    if (!flags.empty()) {
+        DevBuf df((flags.size() + 1) / 2 + 1, c.stream);
+        ZKM_CUDA(cudaMemcpyAsync(df.p, flags.data(), flags.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+        synth_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_out, n, (const int*)df.p, (int)flags.size(), seed);
+        ZKM_LAUNCHED();
+        ZKM_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    ZKM_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+int zkm_b200_synth_trace_device(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, uint64_t* d_out, char** err) {
+    ZKM_API_BEGIN
+    synth_trace_dev(system_id, table, log_n, seed, d_out);
+    ZKM_API_END
+}
+int zkm_b200_synth_trace(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, uint64_t* host_out, char** err) {
+    ZKM_API_BEGIN
+    tables::System sys = tables::make_system(system_id);
+    ZKM_CHECK(table < sys.kinds.size(), "table index out of range");
+    size_t total = (size_t)tables::table_num_columns(sys.kinds[table]) << log_n;
+    DevBuf d(total, ctx().stream);
+    synth_trace_dev(system_id, table, log_n, seed, d.p);
+    d.download(host_out, total);
+    ZKM_API_END
+}
+int zkm_b200_system_shape(int system_id, uint32_t* num_tables, uint32_t* ncols_out, uint32_t max_tables, char** err) {
+    ZKM_API_BEGIN
+    tables::System sys = tables::make_system(system_id);
+    ZKM_CHECK(sys.kinds.size() <= max_tables, "ncols_out too small");
+    *num_tables = (uint32_t)sys.kinds.size();
+    for (size_t t = 0; t < sys.kinds.size(); t++) ncols_out[t] = (uint32_t)tables::table_num_columns(sys.kinds[t]);
     ZKM_API_END
 }
 

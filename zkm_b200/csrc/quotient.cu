@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams q) {
 typedef void (*quotient_kernel_t)(QParams);
 static quotient_kernel_t quotient_kernel_for(int kind) {
     switch (kind) {
-        case tables::T_POSEIDON: return quotient_kernel<tables::T_POSEIDON>;
-        case tables::T_LOGIC: return quotient_kernel<tables::T_LOGIC>;
-        case tables::T_MEMORY: return quotient_kernel<tables::T_MEMORY>;
+#define ZKM_QK(k) case tables::k: return quotient_kernel<tables::k>;
+        ZKM_QK(T_ARITHMETIC) ZKM_QK(T_CPU) ZKM_QK(T_POSEIDON) ZKM_QK(T_POSEIDON_SPONGE) ZKM_QK(T_KECCAK) ZKM_QK(T_KECCAK_SPONGE)
+        ZKM_QK(T_SHA_EXTEND) ZKM_QK(T_SHA_EXTEND_SPONGE) ZKM_QK(T_SHA_COMPRESS) ZKM_QK(T_SHA_COMPRESS_SPONGE) ZKM_QK(T_LOGIC) ZKM_QK(T_MEMORY)
+#undef ZKM_QK
         default:
             throw std::runtime_error(std::string("constraints of table ") + tables::table_name(kind) + " are not available on the device");
     }

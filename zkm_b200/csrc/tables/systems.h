@@ -3,7 +3,7 @@
 // be generated without the MIPS emulator, used for end-to-end prove -> verify parity tests in the
 // spirit of the reference's single-table prove tests (poseidon_stark.rs:751-816, keccak_stark.rs:689-754).
 #pragma once
-#include "registry.h"
+#include "all_stark.h"
 
 namespace zkm {
 namespace tables {
@@ -21,6 +21,8 @@ inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) 
 inline System make_system(int id) {
     System s;
     switch (id) {
+        case SYSTEM_ALL_STARK:
+            return all_stark_system();
         case SYSTEM_LOGIC:
             s.kinds = {T_LOGIC};
             s.ctls.push_back(self_ctl(0, logic::ctl_data(), logic::ctl_filter()));

@@ -72,6 +72,9 @@ def load():
                                                  C.c_uint32, C.POINTER(StarkConfig), C.POINTER(u64p), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_void_p)]
     lib.zkm_b200_free.argtypes = [C.c_void_p]
+    lib.zkm_b200_synth_trace_device.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_synth_trace.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, u64p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_system_shape.argtypes = [C.c_int, u32p, u32p, C.c_uint32, C.POINTER(C.c_void_p)]
     lib.zkm_b200_timer_start.argtypes = [C.POINTER(C.c_void_p)]
     lib.zkm_b200_timer_stop.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
     lib.zkm_b200_profile_enable.argtypes = [C.c_int]
@@ -148,3 +151,22 @@ def prove_system(lib, system_id, traces, roots_before=None, roots_after=None, us
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)
     return proof
+
+
+def system_shape(lib, system_id):
+    n = C.c_uint32()
+    nc = (C.c_uint32 * 32)()
+    err = C.c_void_p()
+    check(lib, lib.zkm_b200_system_shape(system_id, C.byref(n), nc, 32, C.byref(err)), err)
+    return [int(nc[i]) for i in range(n.value)]
+
+
+def synth_traces(lib, system_id, log_heights, seed=0x5EED000000000000):
+    """Host copies of the synthetic traces (generated on the device) for every table of the System."""
+    out = []
+    for t, (nc, lg) in enumerate(zip(system_shape(lib, system_id), log_heights)):
+        a = np.zeros((nc, 1 << lg), dtype=np.uint64)
+        err = C.c_void_p()
+        check(lib, lib.zkm_b200_synth_trace(system_id, t, lg, seed | (t << 16), u64ptr(a), C.byref(err)), err)
+        out.append(a)
+    return out

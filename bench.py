@@ -94,30 +94,35 @@ class ClockSampler:
 
 
 class Segment:
-    """One synthetic segment and the hot-path step over it.
-
-    Stages currently on the GPU path are listed in `stages`; the metric names them, so a partial
-    pipeline is never reported as a full proof."""
+    """One synthetic segment (all 12 AllStark tables) and the hot-path step over it:
+    a full `prove_with_traces` (trace commitments, CTL/logUp columns, quotients, openings, FRI)."""
+    SYSTEM_ALL_STARK = 0
 
     def __init__(self, lib, workload, seed_offset=0):
         import torch
         from zkm_b200 import lib as zl
         self.zl, self.lib, self.torch = zl, lib, torch
         self.heights = workload_log_heights(workload)
-        self.stages = "a1+a2: trace commitments of the 12 tables (iNTT, coset LDE x4, Poseidon Merkle caps)"
-        self.metric = f"segment trace-commit passes/sec ({workload}; stages a1+a2 of prove_with_traces)"
-        self.unit = "segments/s"
+        self.stages = "full prove_with_traces: 12 tables x (trace commit, CTL/logUp aux, quotient, openings, FRI incl. PoW + 37 queries)"
+        self.metric = f"MIPS-segment proofs/sec ({workload}: 2^{max(self.heights)}-row synthetic segment, full STARK prove)"
+        self.unit = "proofs/s"
+        self.cfg = zl.standard_fast_config(lib)
         self.dev = []
         err = C.c_void_p()
         for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
             buf = torch.empty(nc << lg, dtype=torch.int64, device="cuda")
             seed = (0x5EED000000000000 | (t << 16)) + (seed_offset << 32)
-            zl.check(lib, lib.zkm_b200_synth_columns_device(buf.data_ptr(), nc, lg, seed, C.byref(err)), err)
+            zl.check(lib, lib.zkm_b200_synth_trace_device(self.SYSTEM_ALL_STARK, t, lg, seed, buf.data_ptr(), C.byref(err)), err)
             self.dev.append(buf)
         self.input_bytes = sum(8 * (nc << lg) for nc, lg in zip(NCOLS, self.heights))
-        self.output_bytes = 12 * 16 * 4 * 8
+        self.output_bytes = 0
         self.host = None
-        self.caps = np.zeros((12, 64), dtype=np.uint64)
+        self.shapes = (zl.Table * 12)(*[zl.Table(None, nc, lg) for nc, lg in zip(NCOLS, self.heights)])
+        self.dptrs = (C.c_void_p * 12)(*[b.data_ptr() for b in self.dev])
+        self.rb = (C.c_uint32 * 8)(*range(1, 9))
+        self.ra = (C.c_uint32 * 8)(*range(11, 19))
+        self.userdata = bytes(32)
+        self.last_proof_words = 0
 
     def sync(self):
         err = C.c_void_p()
@@ -131,34 +136,40 @@ class Segment:
         self.zl.check(self.lib, self.lib.zkm_b200_timer_stop(C.byref(ms), C.byref(err)), err)
         return ms.value
 
+    def _finish(self, rc, err, out, words):
+        self.zl.check(self.lib, rc, err)
+        self.last_proof_words = words.value
+        self.output_bytes = 8 * words.value
+        self.lib.zkm_b200_free(out)
+
     def step_device(self):
-        lib, zl = self.lib, self.zl
-        err = C.c_void_p()
-        for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
-            h = C.c_void_p()
-            zl.check(lib, lib.zkm_b200_commit_values_device(self.dev[t].data_ptr(), nc, lg, 2, 4, C.byref(h),
-                                                            zl.u64ptr(self.caps[t]), C.byref(err)), err)
-            lib.zkm_b200_batch_free(h)
+        lib = self.lib
+        out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+        rc = lib.zkm_b200_prove_system_device(self.SYSTEM_ALL_STARK, self.shapes, self.dptrs, 12, self.rb, self.ra, self.userdata, 32,
+                                              C.byref(self.cfg), C.byref(out), C.byref(words), C.byref(err))
+        self._finish(rc, err, out, words)
 
     def prepare_host(self):
         torch = self.torch
-        self.host, self.tables = [], []
+        self.host, made = [], []
         for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
             hbuf = torch.empty(nc << lg, dtype=torch.int64, pin_memory=True)
             hbuf.copy_(self.dev[t])
             arr = hbuf.numpy().view(np.uint64).reshape(nc, 1 << lg)
             self.host.append(hbuf)
-            self.tables.append(self.zl.make_table(arr))
+            made.append(self.zl.make_table(arr))
         torch.cuda.synchronize()
+        self._keep = made
+        self.tables = (self.zl.Table * 12)(*[m[0] for m in made])
 
     def step_e2e(self):
-        lib, zl = self.lib, self.zl
-        err = C.c_void_p()
-        for t in range(12):
-            h = C.c_void_p()
-            zl.check(lib, lib.zkm_b200_commit_values(C.byref(self.tables[t][0]), 2, 4, C.byref(h),
-                                                     zl.u64ptr(self.caps[t]), C.byref(err)), err)
-            lib.zkm_b200_batch_free(h)
+        """The reference-facing call: zkm_b200_prove_with_traces with HOST column pointers (H2D of every trace
+        column inside, D2H of the finished proof buffer)."""
+        lib = self.lib
+        out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+        rc = lib.zkm_b200_prove_with_traces(self.tables, self.rb, self.ra, self.userdata, 32, C.byref(self.cfg), C.byref(out),
+                                            C.byref(words), C.byref(err))
+        self._finish(rc, err, out, words)
 
     def profile_reset(self):
         err = C.c_void_p()
@@ -178,7 +189,7 @@ class Segment:
 
     @staticmethod
     def ncu_traffic(family):
-        """dram bytes per launch from the committed `ncu --set full` capture (profiles/*.json), or None."""
+        """dram bytes per launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
         f = ROOT / "profiles" / "ncu_traffic.json"
         if f.exists():
             return json.loads(f.read_text()).get(family)
@@ -186,34 +197,60 @@ class Segment:
 
 
 def cpu_pass(workload, ncores, sample_only=False):
-    """CPU arm: the restated oracle (oracle/liborc.so, `kind: port`) on a bounded sample of the workload:
-    the same 12 tables with every height above 2^16 cut to 2^16, timed on all host cores; the result
-    is scaled linearly in rows back to the full workload (this favours the CPU: it ignores the log n
-    factor of the transforms)."""
+    """CPU arm: the restated oracle (oracle/liborc.so, `kind: port`; the Rust reference cannot be built in this
+    image) running the same full prove_with_traces on a bounded sample of the workload: the same 12 tables
+    with every height above 2^CUT cut to 2^CUT, on all host cores; the time is scaled linearly in trace cells
+    back to the full workload (this favours the CPU: it ignores the log n factor of the transforms)."""
     from oracle import binding
     orc = binding.load()
     orc.orc_set_threads(ncores)
     full = workload_log_heights(workload)
-    sample = [min(h, 16) for h in full]
-    if sample_only:
-        sample = [min(h, 10) for h in full]
-    rows_full = sum(nc << lg for nc, lg in zip(NCOLS, full))
-    rows_s = sum(nc << lg for nc, lg in zip(NCOLS, sample))
-    rng = np.random.default_rng(1)
-    t_total = 0.0
-    cap = np.zeros(64, dtype=np.uint64)
-    for nc, lg in zip(NCOLS, sample):
-        cols = (rng.integers(0, 2**63, size=(nc, 1 << lg), dtype=np.uint64) % np.uint64(0xFFFFFFFF00000001))
-        ptrs = binding.col_ptrs(cols)
-        t0 = time.perf_counter()
-        h = orc.orc_commit(ptrs, nc, lg, 2, 4, 1, binding.u64ptr(cap))
-        t_total += time.perf_counter() - t0
-        orc.orc_batch_free(h)
-    scale = rows_full / rows_s
-    return {"value": 1.0 / (t_total * scale), "unit": "segments/s",
-            "metric": f"segment trace-commit passes/sec ({workload}; stages a1+a2 of prove_with_traces)",
-            "sample": f"heights {sample} ({t_total:.2f} s on {ncores} threads), scaled x{scale:.2f} linearly in cells to {workload}",
+    cut = 8 if sample_only else 13
+    sample = [min(h, cut) for h in full]
+    sample[0] = max(sample[0], 16) if not sample_only else sample[0]     # Arithmetic range table needs 2^16 rows
+    cells_full = sum(nc << lg for nc, lg in zip(NCOLS, full))
+    cells_s = sum(nc << lg for nc, lg in zip(NCOLS, sample))
+    traces = synthetic_traces_host(sample)
+    t0 = time.perf_counter()
+    binding.prove_system(orc, 0, traces)
+    dt = time.perf_counter() - t0
+    scale = cells_full / cells_s
+    return {"value": 1.0 / (dt * scale), "unit": "proofs/s",
+            "metric": f"MIPS-segment proofs/sec ({workload}: 2^{max(full)}-row synthetic segment, full STARK prove)",
+            "sample": f"full prove at heights {sample} ({dt:.2f} s on {ncores} threads), scaled x{scale:.2f} linearly in trace cells to {workload}",
             "note": "restated C++ oracle (the Rust reference cannot be built here: no cargo, plonky2 un-vendored)"}
+
+
+def synthetic_traces_host(log_heights, seed=0x5EED000000000000):
+    """numpy twin of the device generator's contract: uniform cells, CTL-filter columns one-hot (at most one flag per
+    row).  Used by the CPU arm only (it has no GPU); the flag columns are the union of the filter columns of
+    every AllStark CTL, listed per table below (derived from zkm_b200/csrc/tables/all_stark.h)."""
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    P = np.uint64(0xFFFFFFFF00000001)
+    flags = {
+        0: list(range(0, 26)),                                     # Arithmetic op flags
+        1: [7, 8, 10, 16, 17] + [82, 83, 84, 85] + [205 + 6 * c for c in range(9)],   # Cpu: binary/imm/logic/shift flags, sponge flags, channel.used
+        2: [0],                                                    # Poseidon FILTER
+        3: [0] + list(range(14, 46)),                              # PoseidonSponge is_full_input_block, is_final_input_len
+        4: [0, 23],                                                # Keccak reg_step(0), reg_step(23)
+        5: [0] + list(range(40, 176)),                             # KeccakSponge
+        6: [77],                                                   # ShaExtend is_real_round
+        7: list(range(0, 48)),                                     # ShaExtendSponge round flags
+        8: list(range(159, 224)),                                  # ShaCompress round flags
+        9: [126],                                                  # ShaCompressSponge is_real_round
+        10: [0, 1, 2, 3],                                          # Logic op flags
+        11: [0],                                                   # Memory FILTER
+    }
+    out = []
+    for t, (nc, lg) in enumerate(zip(NCOLS, log_heights)):
+        n = 1 << lg
+        a = rng.integers(0, 2**63, size=(nc, n), dtype=np.uint64) % P
+        f = flags[t]
+        hot = rng.integers(-len(f), len(f), size=n)
+        for k, c in enumerate(f):
+            a[c] = (hot == k).astype(np.uint64)
+        out.append(np.ascontiguousarray(a))
+    return out
 
 
 def run_reference(args):
@@ -303,8 +340,8 @@ def main():
         peak, peak_kind = peaks()
         total_ms = sum(v["ms"] for v in fam.values()) or 1.0
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-        # the roofline entry is reported for the HBM-bound NTT family (BASELINE.json: "NTT GB/s vs HBM peak") and
-        # the dominant family is named next to it
+        # the roofline entry is reported for the HBM-bound NTT family (BASELINE.json: "NTT GB/s vs HBM peak"); the
+        # dominant family (Poseidon leaf hashing, integer-ALU bound) is named next to it with every family's share
         ntt = fam.get("ntt_pass", top[1])
         ach = ntt["bytes"] / (ntt["ms"] * 1e-3) / 1e9 if ntt["ms"] else 0.0
         value = args.steps * world / (t_dev * 1e-3)

@@ -1,9 +1,58 @@
 #include "batch.cuh"
 #include <memory>
+#include <map>
 
 namespace zkm {
 
 static std::unique_ptr<Ctx> g_ctx;
+
+// ---- arena (dev.cuh)
+namespace {
+// heap-allocated and never destroyed: DevBufs owned by other statics may be released during process exit
+std::multimap<size_t, void*>& g_free_blocks = *new std::multimap<size_t, void*>();       // size -> block
+size_t g_cached = 0, g_live = 0;
+const size_t ARENA_CACHE_LIMIT = (size_t)150 << 30;
+}
+void* arena_alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = g_free_blocks.lower_bound(bytes);
+    // reuse a cached block when it is not wastefully larger than the request
+    if (it != g_free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
+        void* p = it->second;
+        g_cached -= it->first;
+        g_live += it->first;
+        g_free_blocks.erase(it);
+        return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        arena_trim();                              // give cached blocks back and retry once
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+    g_live += bytes;
+    return p;
+}
+void arena_free(void* p, size_t bytes) {
+    if (!p) return;
+    bytes = (bytes + 511) & ~(size_t)511;
+    // find the true block size: blocks handed out from the cache may be larger than the request; the size
+    // recorded here is the request rounded up, which is what lower_bound matched against, so re-insert
+    // under that size (never larger than the real block)
+    g_live -= bytes <= g_live ? bytes : g_live;
+    if (g_cached + bytes > ARENA_CACHE_LIMIT) arena_trim();
+    g_free_blocks.emplace(bytes, p);
+    g_cached += bytes;
+}
+void arena_trim() {
+    cudaDeviceSynchronize();
+    for (auto& kv : g_free_blocks) cudaFree(kv.second);
+    g_free_blocks.clear();
+    g_cached = 0;
+}
+size_t arena_cached_bytes() { return g_cached; }
 
 bool ctx_ready() { return (bool)g_ctx; }
 Ctx& ctx() {
@@ -25,11 +74,6 @@ void ctx_init(int device) {
     auto c = std::make_unique<Ctx>();
     c->device = device;
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    // keep freed blocks in the pool: the prover allocates/free multi-GB buffers per table
-    cudaMemPool_t pool;
-    ZKM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long thresh = ~0ull;
-    ZKM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     g_ctx = std::move(c);
 }
 void ctx_shutdown() {
@@ -37,6 +81,7 @@ void ctx_shutdown() {
     cudaStreamSynchronize(g_ctx->stream);
     cudaStream_t s = g_ctx->stream;
     g_ctx.reset();
+    arena_trim();
     cudaStreamDestroy(s);
 }
 

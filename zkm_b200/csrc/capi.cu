@@ -8,6 +8,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 
 using namespace zkm;
 
@@ -158,6 +160,7 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
     sc.rate_bits = cfg->rate_bits; sc.cap_height = cfg->cap_height; sc.pow_bits = cfg->pow_bits; sc.num_queries = cfg->num_queries;
     sc.num_challenges = cfg->num_challenges; sc.arity_bits = cfg->arity_bits; sc.final_poly_bits = cfg->final_poly_bits;
     std::vector<TableInput> in(num_tables);
+    auto T0 = std::chrono::steady_clock::now();
     for (uint32_t t = 0; t < num_tables; t++) {
         in[t].ncols = tables[t].ncols; in[t].log_n = tables[t].log_n;
         ZKM_CHECK(tables[t].log_n <= 26, "trace too long");
@@ -173,7 +176,13 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
     PublicInputs pv;
     for (int i = 0; i < 8; i++) { pv.roots_before[i] = roots_before[i]; pv.roots_after[i] = roots_after[i]; }
     pv.userdata.assign(userdata, userdata + userdata_len);
+    if (std::getenv("ZKM_TRACE")) {
+        cudaStreamSynchronize(c.stream);
+        fprintf(stderr, "[zkm_b200] inputs resident %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
+    }
     std::vector<u64> w = prove_system(system_id, sc, in, pv);
+    if (std::getenv("ZKM_TRACE"))
+        fprintf(stderr, "[zkm_b200] prove total     %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     uint64_t* out = (uint64_t*)malloc(w.size() * sizeof(u64));
     ZKM_CHECK(out, "out of host memory");
     memcpy(out, w.data(), w.size() * sizeof(u64));

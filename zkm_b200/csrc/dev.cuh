@@ -28,6 +28,15 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 extern unsigned long long g_launch_count;
 #define ZKM_LAUNCHED() do { ++::zkm::g_launch_count; ZKM_CUDA(cudaGetLastError()); } while (0)
 
+// Device memory arena: blocks come from cudaMalloc once and are then recycled through a size-keyed free
+// list, so a steady-state proof issues no driver allocation calls at all (the stream-ordered driver pool
+// cost 100s of ms per proof in map/unmap work at multi-GB sizes).  All library work runs on one stream, so
+// handing a freed block to the next user is ordered after the previous user's kernels.
+void* arena_alloc(size_t bytes);
+void arena_free(void* p, size_t bytes);
+void arena_trim();                 // cudaFree every cached block
+size_t arena_cached_bytes();
+
 struct DevBuf {
     u64* p = nullptr;
     size_t n = 0;            // elements (u64)
@@ -45,10 +54,10 @@ struct DevBuf {
     void alloc(size_t n_, cudaStream_t s = 0) {
         release();
         n = n_; stream = s;
-        if (n) ZKM_CUDA(cudaMallocAsync((void**)&p, n * sizeof(u64), s));
+        if (n) p = (u64*)arena_alloc(n * sizeof(u64));
     }
     void release() {
-        if (p) { cudaFreeAsync(p, stream); p = nullptr; n = 0; }
+        if (p) { arena_free(p, n * sizeof(u64)); p = nullptr; n = 0; }
     }
     void zero() { if (p) ZKM_CUDA(cudaMemsetAsync(p, 0, n * sizeof(u64), stream)); }
     void upload(const u64* h, size_t cnt, size_t off = 0) {

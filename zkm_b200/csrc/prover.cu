@@ -8,8 +8,28 @@
 #include "poseidon.cuh"
 #include "tables/systems.h"
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace zkm {
+
+// ZKM_TRACE=1: host wall-clock per prover phase on stderr (device idle gaps show up here, not in the
+// per-kernel event timings).
+struct PhaseTimer {
+    bool on; cudaStream_t s; std::chrono::steady_clock::time_point t0; const char* table;
+    PhaseTimer(cudaStream_t s_, const char* table_) : s(s_), table(table_) {
+        on = std::getenv("ZKM_TRACE") != nullptr;
+        if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); }
+    }
+    void mark(const char* phase) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[zkm_b200] %-18s %-22s %9.3f ms\n", table, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // ---------------------------------------------------------------- Challenger
 struct HostChallenger {
@@ -105,6 +125,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
 
     u64 init_state[12];
     ch.compact(init_state);
+    PhaseTimer pt(s, tables::table_name(job.kind));
 
     // ---- auxiliary polynomials (prover.rs:469-522)
     DProgram prog;
@@ -119,6 +140,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         job.values.release();
         batch_from_values_dev(aux, std::move(auxv), naux, log_n, cfg.rate_bits, cfg.cap_height);
     }
+    pt.mark("aux columns+commit");
     ch.observe_cap(aux.tree.cap);
     std::vector<u64> alphas;
     for (int a = 0; a < na; a++) alphas.push_back(ch.get_challenge().v);
@@ -132,6 +154,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         // column a, chunk k (n coefficients) is polynomial 2a + k: already contiguous
         batch_from_coeffs_dev(quot, std::move(q), 2 * na, log_n, cfg.rate_bits, cfg.cap_height);
     }
+    pt.mark("quotient+commit");
     ch.observe_cap(quot.tree.cap);
     gl2 zeta = ch.get_ext_challenge();
     gl g = gl_root_of_unity(log_n);
@@ -160,6 +183,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         eval_polys_at_points(quot.coeffs.p, Q, log_n, pts, 1, h.data(), s);
         for (int i = 0; i < Q; i++) quot_open[i] = gl2(gl(h[i * 2]), gl(h[i * 2 + 1]));
     }
+    pt.mark("openings");
     // observe_openings: zeta batch, zeta_next batch, ctl_zs_first as extension elements (proof.rs:336-367)
     for (gl2 x : local_values) ch.observe(x);
     for (gl2 x : aux_local) ch.observe(x);
@@ -188,6 +212,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         fri_combine(Rv.p, log_n, zeta, zeta_next, v0, v1, v2, a0, a1, cur.p, s);
         coset_intt(c.ntt, cur.p, n, cur.p, n, 2, log_n, s);
     }
+    pt.mark("fri reduce/combine");
     std::vector<FriRound> rounds(arities.size());
     int log_nr = log_n, shift_bits = 0;
     for (size_t r = 0; r < arities.size(); r++) {
@@ -212,6 +237,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         log_nr -= fr.arity_bits;
         shift_bits += fr.arity_bits;
     }
+    pt.mark("fri commit phase");
     size_t nfinal = (size_t)1 << log_nr;
     std::vector<u64> fin(2 * nfinal);
     cur.download(fin.data(), 2 * nfinal);
@@ -229,6 +255,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         int lz = resp.v ? __builtin_clzll(resp.v) : 64;
         ZKM_CHECK(lz >= (int)cfg.pow_bits, "proof-of-work self check failed");
     }
+    pt.mark("fri pow");
     // queries (Appendix A.10)
     const int nq = cfg.num_queries;
     const size_t N = n << cfg.rate_bits;
@@ -273,6 +300,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         }
     }
 
+    pt.mark("fri queries");
     // ---- serialise StarkProofWithMetadata
     W.words(init_state, 12);
     W.cap(job.trace.tree.cap); W.cap(aux.tree.cap); W.cap(quot.tree.cap);
@@ -299,6 +327,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     }
     W.exts(final_poly);
     W.u(pow_witness);
+    pt.mark("serialise");
 }
 
 std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<TableInput>& inputs, const PublicInputs& pv) {
@@ -311,6 +340,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
     ZKM_CHECK(cfg.arity_bits >= 1 && cfg.arity_bits <= 4, "unsupported FRI arity");
     std::vector<tables::TableLayout> layout = tables::derive_layout(sys, cfg.num_challenges);
     std::vector<TableJob> jobs(inputs.size());
+    PhaseTimer pt0(s, "all");
     // trace commitments (prover.rs:144-167)
     for (size_t t = 0; t < inputs.size(); t++) {
         TableJob& j = jobs[t];
@@ -326,6 +356,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
         ntt_inverse(c.ntt, j.values.p, n, coeffs.p, n, j.layout.ncols, j.log_n, s);
         batch_from_coeffs_dev(j.trace, std::move(coeffs), j.layout.ncols, j.log_n, cfg.rate_bits, cfg.cap_height);
     }
+    pt0.mark("trace commitments");
     HostChallenger ch;
     for (TableJob& j : jobs) ch.observe_cap(j.trace.tree.cap);
     for (int i = 0; i < 8; i++) ch.observe((u64)pv.roots_before[i]);

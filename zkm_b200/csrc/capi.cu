@@ -2,7 +2,7 @@
 // the (status, char** err) convention of the reference's own FFI (recursion/src/snark/snarks.rs:7-20).
 #include "../../include/zkm_b200.h"
 #include "batch.cuh"
-#include "poseidon.cuh"
+#include "poseidon_v2.cuh"
 #include "prover.cuh"
 #include "tables/systems.h"
 #include <cstring>
@@ -381,7 +381,7 @@ __global__ void poseidon_states_kernel(u64* st, size_t count) {
     u64 s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = st[i * 12 + k];
-    poseidon_permute(s);
+    poseidon_permute_v2(s);
 #pragma unroll
     for (int k = 0; k < 12; k++) st[i * 12 + k] = s[k];
 }

@@ -15,6 +15,7 @@
 // kept "coset-major": LDE natural index m = 4i + j lives at lde[j*n + i].
 #include "ntt.cuh"
 #include "dev.cuh"
+#include "poseidon_v2.cuh"
 #include <mutex>
 
 namespace zkm {
@@ -43,7 +44,8 @@ struct NttPassParams {
     const u64* in; u64* out;
     size_t in_c, in_b, in_r, in_t, in_z;
     size_t out_c, out_b, out_r, out_t, out_z;
-    int T;                        // tile width (independent transforms per CTA)
+    int T, log_T;                 // tile width (independent transforms per CTA), a power of two
+    u64 w16[8];                   // w_16^e (forward or inverse), e < 8
     int ncols_total;              // valid range for the "t = column" single-pass mode
     int t_is_column;              // single-pass mode: t indexes columns; guard against ncols
     int load_t_fast, store_t_fast;
@@ -53,64 +55,127 @@ struct NttPassParams {
     const u64* tw;                // w_R^k, k < R/2
 };
 
+constexpr int NTT_MAX_THREADS = 1024;
+
+// a * b mod p (canonical) with the hand-scheduled product/reduction of poseidon_v2.cuh
+__device__ __forceinline__ gl fmul(gl a, gl b) { return gl(lz_canon(p2_mul(a.v, b.v))); }
+
+// Size-2^B DIF network on registers; v[j] ends up holding frequency bitrev_B(j).  w16[e] = w_16^e.
+template <int B>
+__device__ __forceinline__ void dft_regs(gl* v, const u64* w16) {
+    constexpr int Q = 1 << B;
+#pragma unroll
+    for (int m = 0; m < B; m++) {
+        const int half = Q >> (m + 1);
+#pragma unroll
+        for (int g = 0; g < (1 << m); g++) {
+#pragma unroll
+            for (int j = 0; j < half; j++) {
+                const int i0 = g * 2 * half + j, i1 = i0 + half;
+                gl a = v[i0], c = v[i1];
+                v[i0] = a + c;
+                gl d = a - c;
+                // w_{2 half}^j = w_16^(j * 16 / (2 half))
+                const int e = j * (16 / (2 * half));
+                v[i1] = (e == 0) ? d : fmul(d, gl(w16[e]));
+            }
+        }
+    }
+}
+
+template <int LOG_R, int DONE, int B>
+__device__ __forceinline__ void radix_step(u64* x, const u64* tw, const NttPassParams& p, int log_T, int tid, int nth) {
+    constexpr int R = 1 << LOG_R, Q = 1 << B;
+    constexpr int LOG_S = LOG_R - DONE - B, S = 1 << LOG_S;       // stride of this step
+    const int T = 1 << log_T, TS = T + 1;
+    const int items = (R / Q) << log_T;
+    for (int idx = tid; idx < items; idx += nth) {
+        const int t = idx & (T - 1), rest = idx >> log_T;
+        const int i2 = rest & (S - 1), blk = rest >> LOG_S;
+        const int base = (blk << (B + LOG_S)) + i2;
+        gl v[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) v[j] = gl(x[(base + (j << LOG_S)) * TS + t]);
+        dft_regs<B>(v, p.w16);
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+            const int k1 = (int)(__brev((unsigned)j) >> (32 - B));
+            gl o = v[j];
+            if (LOG_S > 0 && k1 != 0) o = fmul(o, gl(tw[(i2 * k1) << DONE]));      // w_{Q S}^(i2 k1) = w_R^((R / (Q S)) i2 k1)
+            x[(base + (k1 << LOG_S)) * TS + t] = o.v;
+        }
+    }
+    __syncthreads();
+}
+
+template <int LOG_R, int DONE>
+__device__ __forceinline__ void radix_steps(u64* x, const u64* tw, const NttPassParams& p, int log_T, int tid, int nth) {
+    if constexpr (DONE < LOG_R) {
+        constexpr int REM = LOG_R - DONE;
+        constexpr int B = REM >= 4 ? 4 : REM;
+        radix_step<LOG_R, DONE, B>(x, tw, p, log_T, tid, nth);
+        radix_steps<LOG_R, DONE + B>(x, tw, p, log_T, tid, nth);
+    }
+}
+// position of frequency k after the in-place mixed-radix DIF: digits (radix 16, low digit first) reversed
 template <int LOG_R>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+__device__ __forceinline__ int freq_position(int k) {
+    int pos = 0, done = 0;
+#pragma unroll
+    for (int rem = LOG_R; rem > 0;) {
+        const int b = rem >= 4 ? 4 : rem;
+        const int digit = (k >> done) & ((1 << b) - 1);
+        rem -= b;
+        pos |= digit << rem;
+        done += b;
+    }
+    return pos;
+}
+
+template <int LOG_R>
+__global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams p) {
     constexpr int R = 1 << LOG_R;
     extern __shared__ u64 smem[];
-    const int T = p.T, TS = T + 1;
-    u64* tw = smem;                    // R/2 (at least 1)
-    u64* x = smem + (R / 2 > 0 ? R / 2 : 1);
+    const int T = p.T, TS = T + 1, log_T = p.log_T;
+    u64* tw = smem;                    // R entries: w_R^e
+    u64* x = smem + R;
     const int tid = threadIdx.x, nth = blockDim.x;
     const size_t b = blockIdx.x, c = blockIdx.y, z = blockIdx.z;
-    for (int i = tid; i < R / 2; i += nth) tw[i] = p.tw[i];
+    for (int i = tid; i < R; i += nth) tw[i] = p.tw[i];
     const u64* in = p.in + c * p.in_c + b * p.in_b + z * p.in_z;
     u64* out = p.out + c * p.out_c + b * p.out_b + z * p.out_z;
-    const int total = R * T;
+    const int total = R << log_T;
     int tmax = T;
     if (p.t_is_column) { int rem = p.ncols_total - (int)(b * T); tmax = rem < T ? rem : T; }
     // ---- load (+ optional coset scale) ----
     for (int idx = tid; idx < total; idx += nth) {
         int r, t;
-        if (p.load_t_fast) { r = idx / T; t = idx - r * T; } else { t = idx / R; r = idx - t * R; }
+        if (p.load_t_fast) { r = idx >> log_T; t = idx & (T - 1); } else { t = idx >> LOG_R; r = idx & (R - 1); }
         u64 v = 0;
         if (t < tmax) {
             v = in[(size_t)r * p.in_r + (size_t)t * p.in_t];
             if (p.has_pre) {
                 u64 e = b * p.pre_b + (size_t)r * p.pre_r + (size_t)t * p.pre_t;
-                v = (gl(v) * pow_lookup(p.pre[z], e)).v;
+                v = fmul(gl(v), pow_lookup(p.pre[z], e)).v;
             }
         }
         x[r * TS + t] = v;
     }
     __syncthreads();
-    // ---- radix-2 DIF over r ----
-    const int nbf = (R / 2) * T;
-#pragma unroll 1
-    for (int s = LOG_R - 1; s >= 0; s--) {
-        const int half = 1 << s;
-        for (int idx = tid; idx < nbf; idx += nth) {
-            int j = idx / T, t = idx - j * T;
-            int pos = j & (half - 1);
-            int i0 = ((j >> s) << (s + 1)) + pos;
-            gl a(x[i0 * TS + t]), bb(x[(i0 + half) * TS + t]);
-            gl w(tw[pos << (LOG_R - 1 - s)]);
-            x[i0 * TS + t] = (a + bb).v;
-            x[(i0 + half) * TS + t] = ((a - bb) * w).v;
-        }
-        __syncthreads();
-    }
-    // ---- store: frequency k sits at position bitrev(k) ----
+    // ---- mixed-radix (16) DIF over r, butterflies in registers ----
+    radix_steps<LOG_R, 0>(x, tw, p, log_T, tid, nth);
+    // ---- store ----
     const gl scale(p.scale);
     for (int idx = tid; idx < total; idx += nth) {
         int k, t;
-        if (p.store_t_fast) { k = idx / T; t = idx - k * T; } else { t = idx / R; k = idx - t * R; }
+        if (p.store_t_fast) { k = idx >> log_T; t = idx & (T - 1); } else { t = idx >> LOG_R; k = idx & (R - 1); }
         if (t >= tmax) continue;
-        gl v(x[bitrev32((u32)k, LOG_R) * TS + t]);
+        gl v(x[freq_position<LOG_R>(k) * TS + t]);
         if (p.has_post) {
             u64 e = (b * p.post_b + (size_t)t * p.post_t) * (u64)k;
-            v = v * pow_lookup(p.post, e);
+            v = fmul(v, pow_lookup(p.post, e));
         }
-        if (p.scale != 1) v = v * scale;
+        if (p.scale != 1) v = fmul(v, scale);
         out[(size_t)k * p.out_r + (size_t)t * p.out_t] = v.v;
     }
 }
@@ -125,14 +190,20 @@ static ntt_kernel_t kernel_for(int log_r) {
     throw std::runtime_error("unsupported NTT radix");
 }
 
-static void launch_pass(int log_r, const NttPassParams& p, dim3 grid, cudaStream_t s) {
+static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s) {
     size_t R = (size_t)1 << log_r;
-    size_t smem = ((R / 2 > 0 ? R / 2 : 1) + R * (p.T + 1)) * sizeof(u64);
+    p.log_T = 0;
+    while ((1 << p.log_T) < p.T) p.log_T++;
+    ZKM_CHECK((1 << p.log_T) == p.T, "NTT tile width must be a power of two");
+    size_t smem = (R + R * (p.T + 1)) * sizeof(u64);
     ntt_kernel_t k = kernel_for(log_r);
     // algorithmic bytes of one pass: every element read once and written once
     ProfScope ps("ntt_pass", s, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
     if (smem > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>(p);
+    // one radix-16 work item per thread per step when the tile is large enough (8 warps per SM sub-partition)
+    size_t items = (R >> (log_r >= 4 ? 4 : log_r)) * (size_t)p.T;
+    int threads = items >= 1024 ? 1024 : (items >= 512 ? 512 : 256);
+    k<<<grid, threads, smem, s>>>(p);
     ZKM_LAUNCHED();
 }
 
@@ -165,7 +236,7 @@ static const u64* get_tw(NttTables& T, int log_r, int inverse, cudaStream_t s) {
     auto key = std::make_pair(log_r, inverse);
     auto it = T.impl->tw.find(key);
     if (it != T.impl->tw.end()) return it->second->p;
-    size_t half = log_r ? ((size_t)1 << (log_r - 1)) : 1;
+    size_t half = (size_t)1 << log_r;               // all R powers w_R^e
     std::vector<u64> h(half);
     gl w = gl_root_of_unity(log_r);
     if (inverse) w = gl_inv(w);
@@ -209,6 +280,12 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
     plan(log_n, l1, l2, T);
     size_t n = (size_t)1 << log_n;
     NttPassParams p = {};
+    {
+        gl w = gl_root_of_unity(4);
+        if (inverse) w = gl_inv(w);
+        gl cur = gl::one();
+        for (int e = 0; e < 8; e++) { p.w16[e] = cur.v; cur = cur * w; }
+    }
     p.has_pre = pre != nullptr;
     if (pre) for (int z = 0; z < nz; z++) p.pre[z] = pre[z];
     if (l2 == 0) {
@@ -250,6 +327,7 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         launch_pass(l1, p, dim3((unsigned)(n2 / T), nc, nz), s);
         // pass B: scratch rows k1 (contiguous i2) -> out[k1 + n1*k2]
         NttPassParams q = {};
+        for (int e = 0; e < 8; e++) q.w16[e] = p.w16[e];
         q.in = scratch.p; q.out = out + (size_t)c0 * out_cs;
         q.in_c = (size_t)nz * n; q.in_b = (size_t)T * n2; q.in_r = 1; q.in_t = n2; q.in_z = n;
         q.out_c = out_cs; q.out_b = T; q.out_r = n1; q.out_t = 1; q.out_z = out_zs;

@@ -1,0 +1,113 @@
+// Device-tuned Goldilocks Poseidon permutation (same function as poseidon.cuh poseidon_permute; the
+// portable version stays for the host-side transcript).  Differences, all found by reading the SASS of
+// the portable version (tools/micro/poseidon_bench.cu):
+//  * 64x64->128 product as 4 IMAD.WIDE + one IADD3 carry chain, and the 2^64 = 2^32-1, 2^96 = -1
+//    reduction as a second carry chain (no ISETP/SEL pairs, no IMAD.X/IMAD.MOV on the FMA pipe);
+//  * the MDS row sums as explicit mad.wide.u32 accumulations (the compiler strength-reduces the small
+//    circulant constants into shift/add sequences on 64-bit values, 2.4x more instructions);
+//  * values stay non-canonical residues in [0, 2^64) until the end.
+#pragma once
+#include "poseidon.cuh"
+
+namespace zkm {
+#ifdef __CUDACC__
+
+// (a * b) mod p as a lazy residue in [0, 2^64)
+__device__ __forceinline__ u64 p2_mul(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 o0, o1;
+    asm("{\n\t.reg .u64 p00,p01,p10,p11;\n\t.reg .u32 r0,r1,r2,r3,t1,u1,u2,v1,v2,w2,w3,s0,s1,t0,tt1,b,c,m;\n\t"
+        "mul.wide.u32 p00, %2, %4;\n\tmul.wide.u32 p01, %2, %5;\n\tmul.wide.u32 p10, %3, %4;\n\tmul.wide.u32 p11, %3, %5;\n\t"
+        "mov.b64 {r0, t1}, p00;\n\tmov.b64 {u1, u2}, p01;\n\tmov.b64 {v1, v2}, p10;\n\tmov.b64 {w2, w3}, p11;\n\t"
+        "add.cc.u32 r1, t1, u1;\n\taddc.cc.u32 r2, u2, w2;\n\taddc.u32 r3, w3, 0;\n\t"
+        "add.cc.u32 r1, r1, v1;\n\taddc.cc.u32 r2, r2, v2;\n\taddc.u32 r3, r3, 0;\n\t"
+        // reduce r3:r2:r1:r0 :  lo - (r2 + r3) + (r2 << 32), each wrap of 2^64 fixed with -/+ (2^32 - 1)
+        "add.cc.u32 s0, r2, r3;\n\taddc.u32 s1, 0, 0;\n\t"
+        "sub.cc.u32 t0, r0, s0;\n\tsubc.cc.u32 tt1, r1, s1;\n\tsubc.u32 b, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
+        "add.cc.u32 tt1, tt1, r2;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return (u64)o0 | ((u64)o1 << 32);
+}
+// a + c for a lazy residue a and a canonical constant c
+__device__ __forceinline__ u64 p2_add_canon(u64 a, u64 c) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), c0 = (u32)c, c1 = (u32)(c >> 32);
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 t0,t1,cy,m;\n\t"
+        "add.cc.u32 t0, %2, %4;\n\taddc.cc.u32 t1, %3, %5;\n\taddc.u32 cy, 0, 0;\n\t"
+        "sub.u32 m, 0, cy;\n\t"
+        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, t1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(c0), "r"(c1));
+    return (u64)o0 | ((u64)o1 << 32);
+}
+__device__ __forceinline__ u64 p2_sbox7(u64 x) {
+    u64 x2 = p2_mul(x, x);
+    u64 x3 = p2_mul(x2, x);
+    u64 x4 = p2_mul(x2, x2);
+    return p2_mul(x3, x4);
+}
+__device__ __forceinline__ u64 p2_madw(u32 a, u32 c, u64 acc) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(c), "l"(acc));
+    return r;
+}
+// out[r] = sum_i s[(i+r)%12] * CIRC[i] + (r == 0 ? 8 s[0] : 0)   (constants.rs:104-105)
+__device__ __forceinline__ void p2_mds(u64* s) {
+    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    u32 lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        u64 al = 0, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            al = p2_madw(lo[(i + r) % 12], C[i], al);
+            ah = p2_madw(hi[(i + r) % 12], C[i], ah);
+        }
+        if (r == 0) { al = p2_madw(lo[0], 8u, al); ah = p2_madw(hi[0], 8u, ah); }
+        // value = al + ah * 2^32 < 2^75: (h : l1 : l0) with h = ah >> 32 + carry, reduce h*2^64 = h*(2^32-1)
+        u32 al0 = (u32)al, al1 = (u32)(al >> 32), ah0 = (u32)ah, ah1 = (u32)(ah >> 32);
+        u32 o0, o1;
+        asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
+            "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"            // (h : l1 : al0)
+            "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"  // h * (2^32 - 1) < 2^43
+            "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
+            "sub.u32 m, 0, cy;\n\t"
+            "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
+            : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
+        s[r] = (u64)o0 | ((u64)o1 << 32);
+    }
+}
+
+__device__ __forceinline__ void poseidon_permute_v2(u64* s) {
+    int rc = 0;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
+        rc += 12;
+        p2_mds(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
+        rc += 12;
+        s[0] = p2_sbox7(s[0]);
+        p2_mds(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
+        rc += 12;
+        p2_mds(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
+#endif
+}  // namespace zkm

@@ -98,10 +98,11 @@ class Segment:
     a full `prove_with_traces` (trace commitments, CTL/logUp columns, quotients, openings, FRI)."""
     SYSTEM_ALL_STARK = 0
 
-    def __init__(self, lib, workload, seed_offset=0):
+    def __init__(self, lib, workload, seed_offset=0, rank=0, world=1):
         import torch
         from zkm_b200 import lib as zl
         self.zl, self.lib, self.torch = zl, lib, torch
+        self.rank, self.world = rank, world
         self.heights = workload_log_heights(workload)
         self.stages = "full prove_with_traces: 12 tables x (trace commit, CTL/logUp aux, quotient, openings, FRI incl. PoW + 37 queries)"
         self.metric = f"MIPS-segment proofs/sec ({workload}: 2^{max(self.heights)}-row synthetic segment, full STARK prove)"
@@ -136,11 +137,13 @@ class Segment:
         self.zl.check(self.lib, self.lib.zkm_b200_timer_stop(C.byref(ms), C.byref(err)), err)
         return ms.value
 
-    def _finish(self, rc, err, out, words):
+    def _finish(self, rc, err, out, words, keep=False):
         self.zl.check(self.lib, rc, err)
         self.last_proof_words = words.value
         self.output_bytes = 8 * words.value
+        proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy() if keep else None
         self.lib.zkm_b200_free(out)
+        return proof
 
     def step_device(self):
         lib = self.lib
@@ -169,7 +172,11 @@ class Segment:
         out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
         rc = lib.zkm_b200_prove_with_traces(self.tables, self.rb, self.ra, self.userdata, 32, C.byref(self.cfg), C.byref(out),
                                             C.byref(words), C.byref(err))
-        self._finish(rc, err, out, words)
+        proof = self._finish(rc, err, out, words, keep=self.world > 1)
+        if self.world > 1:
+            # the path's only exchange: finished proofs gathered on rank 0 (NCCL)
+            from zkm_b200 import multi
+            multi.gather_proofs([proof], [self.rank], self.world)
 
     def profile_reset(self):
         err = C.c_void_p()
@@ -304,7 +311,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = zl.init(local)
-    seg = Segment(lib, args.workload, seed_offset=rank)
+    seg = Segment(lib, args.workload, seed_offset=rank, rank=rank, world=world)
 
     def barrier():
         if world > 1:

@@ -18,7 +18,7 @@ __device__ __forceinline__ size_t lde_pos_of_leaf(u32 leaf, int log_n, int rate_
     return ((size_t)j << log_n) + i;
 }
 
-__global__ void __launch_bounds__(128) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
+__global__ void __launch_bounds__(128, 6) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
                                                             int rate_bits, u64* __restrict__ dig) {
     const size_t N = (size_t)1 << (log_n + rate_bits);
     size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,13 +39,13 @@ __global__ void __launch_bounds__(128) lde_leaf_hash_kernel(const u64* __restric
         for (; c + 8 <= ncols; c += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) s[k] = __ldg(col + (size_t)(c + k) * cs);
-            poseidon_permute_v2(s);
+            poseidon_permute_v3(s);
         }
         if (c < ncols) {
             int rem = ncols - c;
 #pragma unroll
             for (int k = 0; k < 8; k++) if (k < rem) s[k] = __ldg(col + (size_t)(c + k) * cs);
-            poseidon_permute_v2(s);
+            poseidon_permute_v3(s);
         }
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + (size_t)leaf * 4);
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) lde_leaf_hash_kernel(const u64* __restric
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-__global__ void __launch_bounds__(128) rows_leaf_hash_kernel(const u64* __restrict__ rows, int width, size_t num_leaves,
+__global__ void __launch_bounds__(128, 6) rows_leaf_hash_kernel(const u64* __restrict__ rows, int width, size_t num_leaves,
                                                              u64* __restrict__ dig) {
     size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= num_leaves) return;
@@ -69,13 +69,13 @@ __global__ void __launch_bounds__(128) rows_leaf_hash_kernel(const u64* __restri
         for (; c + 8 <= width; c += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) s[k] = row[c + k];
-            poseidon_permute_v2(s);
+            poseidon_permute_v3(s);
         }
         if (c < width) {
             int rem = width - c;
 #pragma unroll
             for (int k = 0; k < 8; k++) if (k < rem) s[k] = row[c + k];
-            poseidon_permute_v2(s);
+            poseidon_permute_v3(s);
         }
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + leaf * 4);
@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(128) rows_leaf_hash_kernel(const u64* __restri
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-__global__ void __launch_bounds__(128) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+__global__ void __launch_bounds__(128, 6) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parents) return;
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
     ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
     u64 s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
-    poseidon_permute_v2(s);
+    poseidon_permute_v3(s);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(parent + i * 4);
     o[0] = make_ulonglong2(s[0], s[1]);
     o[1] = make_ulonglong2(s[2], s[3]);

@@ -82,6 +82,67 @@ __device__ __forceinline__ void p2_mds(u64* s) {
     }
 }
 
+// ---- MDS on the FP64 pipe: the row sums  sum_i C[i] * (32-bit half)  are < 2^40, i.e. exact in double
+// arithmetic.  DFMA issues on its own pipe, so the 288 multiply-accumulates per layer stop competing with
+// the S-box integer work for the FMA/ALU pipes.  u32 <-> double conversions are the 2^52 magic-number
+// trick (one DADD each), never I2F/F2I.
+__device__ __forceinline__ double p3_u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+__device__ __forceinline__ void p3_mds(u64* s) {
+    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    double lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double al = lo[r] * C[0], ah = hi[r] * C[0];
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            al = fma(lo[(i + r) % 12], C[i], al);
+            ah = fma(hi[(i + r) % 12], C[i], ah);
+        }
+        if (r == 0) { al = fma(lo[0], 8.0, al); ah = fma(hi[0], 8.0, ah); }
+        double tl = al + 4503599627370496.0, th = ah + 4503599627370496.0;
+        u32 al0 = (u32)__double2loint(tl), al1 = (u32)__double2hiint(tl) & 0xfffffu;
+        u32 ah0 = (u32)__double2loint(th), ah1 = (u32)__double2hiint(th) & 0xfffffu;
+        u32 o0, o1;
+        asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
+            "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"
+            "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"
+            "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
+            "sub.u32 m, 0, cy;\n\t"
+            "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
+            : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
+        s[r] = (u64)o0 | ((u64)o1 << 32);
+    }
+}
+__device__ __forceinline__ void poseidon_permute_v3(u64* s) {
+    int rc = 0;
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
+        rc += 12;
+        p3_mds(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
+        rc += 12;
+        s[0] = p2_sbox7(s[0]);
+        p3_mds(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
+        rc += 12;
+        p3_mds(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
+
 __device__ __forceinline__ void poseidon_permute_v2(u64* s) {
     int rc = 0;
 #pragma unroll 1

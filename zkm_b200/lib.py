@@ -31,7 +31,7 @@ EXPORTS = [
     "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 

@@ -74,12 +74,15 @@ void ctx_init(int device) {
     auto c = std::make_unique<Ctx>();
     c->device = device;
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     g_ctx = std::move(c);
 }
 void ctx_shutdown() {
     if (!g_ctx) return;
     cudaStreamSynchronize(g_ctx->stream);
     cudaStream_t s = g_ctx->stream;
+    cudaStreamSynchronize(g_ctx->copy_stream);
+    cudaStreamDestroy(g_ctx->copy_stream);
     g_ctx.reset();
     arena_trim();
     cudaStreamDestroy(s);

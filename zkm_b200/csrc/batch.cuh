@@ -11,6 +11,7 @@ namespace zkm {
 struct Ctx {
     int device = -1;
     cudaStream_t stream = 0;
+    cudaStream_t copy_stream = 0;          // host->device trace uploads, overlapped with the commitments
     NttTables ntt;
 };
 Ctx& ctx();                    // throws if zkm_b200_init has not succeeded

@@ -170,9 +170,23 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
             in[t].values.alloc((size_t)tables[t].ncols * n, c.stream);
             ZKM_CUDA(cudaMemcpyAsync(in[t].values.p, d_tables[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream));
         } else {
-            in[t].values = upload_table(&tables[t]);
+            // upload on the copy stream: with pinned host columns the copies of table t+1.. run while table t is
+            // being committed; the prover waits on `ready` before touching the buffer
+            const zkm_table_t* tb = &tables[t];
+            ZKM_CHECK(tb->cols && tb->ncols > 0, "null/empty table");
+            in[t].values.alloc((size_t)tb->ncols * n, c.stream);
+            for (uint32_t i = 0; i < tb->ncols; i++) {
+                ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
+                ZKM_CUDA(cudaMemcpyAsync(in[t].values.p + (size_t)i * n, tb->cols[i], n * sizeof(u64), cudaMemcpyHostToDevice, c.copy_stream));
+            }
+            ZKM_CUDA(cudaEventCreateWithFlags(&in[t].ready, cudaEventDisableTiming));
+            ZKM_CUDA(cudaEventRecord(in[t].ready, c.copy_stream));
         }
     }
+    struct EventGuard {
+        std::vector<TableInput>& v; cudaStream_t cs;
+        ~EventGuard() { cudaStreamSynchronize(cs); for (auto& x : v) if (x.ready) cudaEventDestroy(x.ready); }
+    } guard{in, c.copy_stream};
     PublicInputs pv;
     for (int i = 0; i < 8; i++) { pv.roots_before[i] = roots_before[i]; pv.roots_after[i] = roots_after[i]; }
     pv.userdata.assign(userdata, userdata + userdata_len);

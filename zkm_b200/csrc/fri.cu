@@ -68,6 +68,44 @@ __global__ void __launch_bounds__(256) fri_reduce_kernel(ReduceParams p) {
     p.out[4 * p.n + i] = accz.a.v; p.out[5 * p.n + i] = accz.b.v;
 }
 
+// Short polynomials (n < 2^12, the 2^6-row tables with up to 2431 columns): one CTA per coefficient index,
+// threads stride over the columns, tree reduction in shared memory.
+__global__ void __launch_bounds__(256) fri_reduce_small_kernel(ReduceParams p) {
+    __shared__ u64 sh[3][256][2];
+    const size_t i = blockIdx.x;
+    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(p.apow);
+    gl2 acc0 = gl2::zero(), acc1 = gl2::zero(), accz = gl2::zero();
+    const int total = p.ntr + p.nax + p.nqt;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        ulonglong2 a = __ldg(ap + k);
+        gl2 al = mk2(a.x, a.y);
+        if (k < p.ntr) {
+            gl2 t = al * gl(__ldg(p.tr + (size_t)k * p.n + i));
+            acc0 = acc0 + t; acc1 = acc1 + t;
+        } else if (k < p.ntr + p.nax) {
+            int c = k - p.ntr;
+            gl v(__ldg(p.ax + (size_t)c * p.n + i));
+            gl2 t = al * v;
+            acc0 = acc0 + t; acc1 = acc1 + t;
+            if (c >= p.zstart) { ulonglong2 b = __ldg(ap + (c - p.zstart)); accz = accz + mk2(b.x, b.y) * v; }
+        } else {
+            acc0 = acc0 + al * gl(__ldg(p.qt + (size_t)(k - p.ntr - p.nax) * p.n + i));
+        }
+    }
+    const int t = threadIdx.x;
+    sh[0][t][0] = acc0.a.v; sh[0][t][1] = acc0.b.v; sh[1][t][0] = acc1.a.v; sh[1][t][1] = acc1.b.v; sh[2][t][0] = accz.a.v; sh[2][t][1] = accz.b.v;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (t < off)
+            for (int q = 0; q < 3; q++) {
+                gl2 r = mk2(sh[q][t][0], sh[q][t][1]) + mk2(sh[q][t + off][0], sh[q][t + off][1]);
+                sh[q][t][0] = r.a.v; sh[q][t][1] = r.b.v;
+            }
+        __syncthreads();
+    }
+    if (t < 6) p.out[(size_t)t * p.n + i] = sh[t >> 1][0][t & 1];
+}
+
 // ---- 2. pointwise combination on the coset 7*H_n ---------------------------------------------
 struct CombineParams {
     const u64* r;                 // 6 columns of n: values of R0, R1, R2 on 7*w_n^i
@@ -152,7 +190,8 @@ void fri_reduce_batches(const Batch& trace, const Batch& aux, const Batch& quot,
     p.qt = quot.coeffs.p; p.nqt = quot.ncols;
     p.apow = ap.p; p.n = n; p.out = d_out;
     ProfScope ps("fri_reduce", s, 8.0 * (double)n * (trace.ncols + aux.ncols + quot.ncols) + 48.0 * (double)n);
-    fri_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+    if (n < 4096) fri_reduce_small_kernel<<<(unsigned)n, 256, 0, s>>>(p);
+    else fri_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
     ZKM_LAUNCHED();
     ZKM_CUDA(cudaStreamSynchronize(s));           // h / ap lifetime
 }

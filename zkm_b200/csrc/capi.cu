@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include <cstdio>
 
 using namespace zkm;
@@ -170,27 +173,57 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
             in[t].values.alloc((size_t)tables[t].ncols * n, c.stream);
             ZKM_CUDA(cudaMemcpyAsync(in[t].values.p, d_tables[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream));
         } else {
-            // upload on the copy stream: with pinned host columns the copies of table t+1.. run while table t is
-            // being committed; the prover waits on `ready` before touching the buffer
+            // uploads run on the copy stream from a helper thread (cudaMemcpyAsync blocks the calling thread for
+            // pageable and, on this platform, also for pinned sources), so table t+1.. stream in while table t is
+            // being committed; the prover waits on `ready` before touching a buffer
             const zkm_table_t* tb = &tables[t];
             ZKM_CHECK(tb->cols && tb->ncols > 0, "null/empty table");
+            for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
             in[t].values.alloc((size_t)tb->ncols * n, c.stream);
-            for (uint32_t i = 0; i < tb->ncols; i++) {
-                ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
-                ZKM_CUDA(cudaMemcpyAsync(in[t].values.p + (size_t)i * n, tb->cols[i], n * sizeof(u64), cudaMemcpyHostToDevice, c.copy_stream));
-            }
             ZKM_CUDA(cudaEventCreateWithFlags(&in[t].ready, cudaEventDisableTiming));
-            ZKM_CUDA(cudaEventRecord(in[t].ready, c.copy_stream));
         }
     }
+    struct Uploader {
+        std::thread th; std::mutex mu; std::condition_variable cv; int recorded = 0; std::string error;
+        ~Uploader() { if (th.joinable()) th.join(); }
+    } up;
     struct EventGuard {
-        std::vector<TableInput>& v; cudaStream_t cs;
-        ~EventGuard() { cudaStreamSynchronize(cs); for (auto& x : v) if (x.ready) cudaEventDestroy(x.ready); }
-    } guard{in, c.copy_stream};
+        std::vector<TableInput>& v; cudaStream_t cs; Uploader& u;
+        ~EventGuard() { if (u.th.joinable()) u.th.join(); cudaStreamSynchronize(cs); for (auto& x : v) if (x.ready) cudaEventDestroy(x.ready); }
+    } guard{in, c.copy_stream, up};
+    if (!d_tables) {
+        int device = c.device;
+        cudaStream_t cs = c.copy_stream;
+        std::vector<u64*> dst(num_tables);
+        for (uint32_t t = 0; t < num_tables; t++) dst[t] = in[t].values.p;
+        std::vector<cudaEvent_t> evs(num_tables);
+        for (uint32_t t = 0; t < num_tables; t++) evs[t] = in[t].ready;
+        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs] {
+            cudaSetDevice(device);
+            for (uint32_t t = 0; t < num_tables; t++) {
+                size_t n = (size_t)1 << tables[t].log_n;
+                cudaError_t e = cudaSuccess;
+                for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++)
+                    e = cudaMemcpyAsync(dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                if (e == cudaSuccess) e = cudaEventRecord(evs[t], cs);
+                std::lock_guard<std::mutex> g(up.mu);
+                if (e != cudaSuccess && up.error.empty()) up.error = cudaGetErrorString(e);
+                up.recorded = (int)t + 1;
+                up.cv.notify_all();
+            }
+        });
+        for (uint32_t t = 0; t < num_tables; t++)
+            in[t].wait_recorded = [&up, t] {
+                std::unique_lock<std::mutex> lk(up.mu);
+                up.cv.wait(lk, [&] { return up.recorded > (int)t; });
+                if (!up.error.empty()) throw CudaError("trace upload failed: " + up.error);
+            };
+    }
     PublicInputs pv;
     for (int i = 0; i < 8; i++) { pv.roots_before[i] = roots_before[i]; pv.roots_after[i] = roots_after[i]; }
     pv.userdata.assign(userdata, userdata + userdata_len);
     if (std::getenv("ZKM_TRACE")) {
+        fprintf(stderr, "[zkm_b200] uploads issued  %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
         cudaStreamSynchronize(c.stream);
         fprintf(stderr, "[zkm_b200] inputs resident %9.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count());
     }

@@ -352,6 +352,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
         ZKM_CHECK(j.log_n + (int)cfg.rate_bits >= (int)cfg.cap_height && j.log_n >= 1, "trace too short");
         size_t n = (size_t)1 << j.log_n;
         j.values = std::move(inputs[t].values);
+        if (inputs[t].wait_recorded) inputs[t].wait_recorded();
         if (inputs[t].ready) ZKM_CUDA(cudaStreamWaitEvent(s, inputs[t].ready, 0));
         DevBuf coeffs((size_t)j.layout.ncols * n, s);
         ntt_inverse(c.ntt, j.values.p, n, coeffs.p, n, j.layout.ncols, j.log_n, s);

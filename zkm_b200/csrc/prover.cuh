@@ -2,6 +2,7 @@
 #pragma once
 #include "aux.cuh"
 #include <vector>
+#include <functional>
 
 namespace zkm {
 
@@ -11,7 +12,8 @@ struct StarkCfg {                 // StarkConfig / FriConfig (reference prover/s
 struct TableInput {
     DevBuf values;                // ncols x 2^log_n trace values on H, column-major, on the device (consumed)
     int ncols = 0, log_n = 0;
-    cudaEvent_t ready = nullptr;  // if set: recorded on another stream once `values` is filled; the prover waits on it
+    cudaEvent_t ready = nullptr;  // if set: recorded on the copy stream once `values` is filled; the prover waits on it
+    std::function<void()> wait_recorded;   // if set: blocks the host until `ready` has been recorded (uploader thread)
 };
 struct PublicInputs {             // PublicValues (proof.rs:52-61)
     uint32_t roots_before[8], roots_after[8];

@@ -59,6 +59,19 @@ __global__ void __launch_bounds__(128, MINB) k_perm_v3(const u64* __restrict__ i
 #pragma unroll
     for (int k = 0; k < 12; k++) out[k * count + i] = s[k];
 }
+template <int V, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_perm_vx(const u64* __restrict__ in, u64* __restrict__ out, size_t count, int reps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = in[k * count + i];
+    for (int r = 0; r < reps; r++) {
+        if (V == 4) poseidon_permute_v4(s); else poseidon_permute_v6(s);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[k * count + i] = s[k];
+}
 template <class F> void timeit(const char* name, F f, size_t count, int reps) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9;
@@ -125,6 +138,16 @@ int main() {
     }
     timeit("v3 fp64-mds lb(128,6)", [&] { k_perm_v3<6><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v3 fp64-mds lb(128,8)", [&] { k_perm_v3<8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    auto check = [&](const char* name) {
+        cudaMemcpy(got.data(), dout, got.size() * 8, cudaMemcpyDeviceToHost);
+        size_t bad = 0;
+        for (size_t i = 0; i < 4096; i++) for (int k = 0; k < 12; k++) if (got[k * count + i] != ref[k * 4096 + i]) bad++;
+        printf("%s mismatches=%zu\n", name, bad);
+    };
+    timeit("v4 single-loop lb(128,6)", [&] { k_perm_vx<4, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v4");
+    timeit("v4 single-loop lb(128,8)", [&] { k_perm_vx<4, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v6 rolled sbox lb(128,6)", [&] { k_perm_vx<6, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v6");
+    timeit("v6 rolled sbox lb(128,8)", [&] { k_perm_vx<6, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v2 x2 states/thread", [&] { k_perm_x2<<<g / 2, 128>>>(din, dout, count, reps); }, count, reps);
 #endif
     return 0;

@@ -143,6 +143,54 @@ __device__ __forceinline__ void poseidon_permute_v3(u64* s) {
     for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
 }
 
+// ---- compact-code variants: the fully unrolled permutation is ~70 KB of SASS and the kernels built on it
+// stall on instruction fetch (ncu: "no instruction" is the top stall reason).  v4 keeps ONE copy of the MDS
+// and S-box code in a single 30-iteration round loop; v5 additionally shares the S-box code through a
+// non-inlined 4-wide helper.
+__device__ __forceinline__ void poseidon_permute_v4(u64* s) {
+    int rc = 0;
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
+        rc += 12;
+        s[0] = p2_sbox7(s[0]);
+        if (full) {
+#pragma unroll
+            for (int i = 1; i < 12; i++) s[i] = p2_sbox7(s[i]);
+        }
+        p3_mds(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
+// v6: the 12-wide S-box layer as a rolled loop of 3 x 4 with a register rotation (code ~370 instead of ~880
+// instructions): 0.904 G perm/s.  (Rolling the MDS the same way, or sharing the S-box through a non-inlined
+// helper, measured slower: 0.71 / 0.86.)
+__device__ __forceinline__ void p6_sbox_layer(u64* s) {
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        u64 a = p2_sbox7(s[0]), b = p2_sbox7(s[1]), c = p2_sbox7(s[2]), d = p2_sbox7(s[3]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+        s[8] = a; s[9] = b; s[10] = c; s[11] = d;
+    }
+}
+__device__ __forceinline__ void poseidon_permute_v6(u64* s) {
+    int rc = 0;
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
+        rc += 12;
+        if (full) p6_sbox_layer(s); else s[0] = p2_sbox7(s[0]);
+        p3_mds(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
 __device__ __forceinline__ void poseidon_permute_v2(u64* s) {
     int rc = 0;
 #pragma unroll 1

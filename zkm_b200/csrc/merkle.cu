@@ -35,16 +35,12 @@ __global__ void __launch_bounds__(128, 6) lde_leaf_hash_kernel(const u64* __rest
 #pragma unroll
         for (int k = 0; k < 4; k++) if (k < ncols) s[k] = col[(size_t)k * cs];
     } else {
-        int c = 0;
-        for (; c + 8 <= ncols; c += 8) {
+        // one copy of the permutation code (instruction-cache footprint): the ragged last chunk is handled by
+        // predicated loads inside the same loop
+#pragma unroll 1
+        for (int c = 0; c < ncols; c += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = __ldg(col + (size_t)(c + k) * cs);
-            poseidon_permute_v6(s);
-        }
-        if (c < ncols) {
-            int rem = ncols - c;
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (k < rem) s[k] = __ldg(col + (size_t)(c + k) * cs);
+            for (int k = 0; k < 8; k++) if (c + k < ncols) s[k] = __ldg(col + (size_t)(c + k) * cs);
             poseidon_permute_v6(s);
         }
     }
@@ -65,16 +61,10 @@ __global__ void __launch_bounds__(128, 6) rows_leaf_hash_kernel(const u64* __res
 #pragma unroll
         for (int k = 0; k < 4; k++) if (k < width) s[k] = row[k];
     } else {
-        int c = 0;
-        for (; c + 8 <= width; c += 8) {
+#pragma unroll 1
+        for (int c = 0; c < width; c += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = row[c + k];
-            poseidon_permute_v6(s);
-        }
-        if (c < width) {
-            int rem = width - c;
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (k < rem) s[k] = row[c + k];
+            for (int k = 0; k < 8; k++) if (c + k < width) s[k] = row[c + k];
             poseidon_permute_v6(s);
         }
     }

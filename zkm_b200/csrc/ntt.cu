@@ -83,39 +83,43 @@ __device__ __forceinline__ void dft_regs(gl* v, const u64* w16) {
     }
 }
 
-template <int LOG_R, int DONE, int B>
-__device__ __forceinline__ void radix_step(u64* x, const u64* tw, const NttPassParams& p, int log_T, int tid, int nth) {
+// One radix-2^B step of the in-place DIF at stride 2^log_S (blocks of 2^(B + log_S) points); `done` = number
+// of index bits already processed.  log_S / done are run-time values so that all radix-16 steps of a pass
+// share ONE copy of the butterfly code (the fully specialised version was instruction-fetch bound).
+template <int LOG_R, int B>
+__device__ __forceinline__ void radix_step(u64* x, const u64* tw, const NttPassParams& p, int log_T, int tid, int nth, int log_S, int done) {
     constexpr int R = 1 << LOG_R, Q = 1 << B;
-    constexpr int LOG_S = LOG_R - DONE - B, S = 1 << LOG_S;       // stride of this step
+    const int S = 1 << log_S;
     const int T = 1 << log_T, TS = T + 1;
     const int items = (R / Q) << log_T;
     for (int idx = tid; idx < items; idx += nth) {
         const int t = idx & (T - 1), rest = idx >> log_T;
-        const int i2 = rest & (S - 1), blk = rest >> LOG_S;
-        const int base = (blk << (B + LOG_S)) + i2;
+        const int i2 = rest & (S - 1), blk = rest >> log_S;
+        const int base = (blk << (B + log_S)) + i2;
         gl v[Q];
 #pragma unroll
-        for (int j = 0; j < Q; j++) v[j] = gl(x[(base + (j << LOG_S)) * TS + t]);
+        for (int j = 0; j < Q; j++) v[j] = gl(x[(base + (j << log_S)) * TS + t]);
         dft_regs<B>(v, p.w16);
 #pragma unroll
         for (int j = 0; j < Q; j++) {
             const int k1 = (int)(__brev((unsigned)j) >> (32 - B));
             gl o = v[j];
-            if (LOG_S > 0 && k1 != 0) o = fmul(o, gl(tw[(i2 * k1) << DONE]));      // w_{Q S}^(i2 k1) = w_R^((R / (Q S)) i2 k1)
-            x[(base + (k1 << LOG_S)) * TS + t] = o.v;
+            if (k1 != 0 && log_S > 0) o = fmul(o, gl(tw[(i2 * k1) << done]));      // w_{Q S}^(i2 k1) = w_R^((R / (Q S)) i2 k1)
+            x[(base + (k1 << log_S)) * TS + t] = o.v;
         }
     }
     __syncthreads();
 }
 
-template <int LOG_R, int DONE>
+template <int LOG_R>
 __device__ __forceinline__ void radix_steps(u64* x, const u64* tw, const NttPassParams& p, int log_T, int tid, int nth) {
-    if constexpr (DONE < LOG_R) {
-        constexpr int REM = LOG_R - DONE;
-        constexpr int B = REM >= 4 ? 4 : REM;
-        radix_step<LOG_R, DONE, B>(x, tw, p, log_T, tid, nth);
-        radix_steps<LOG_R, DONE + B>(x, tw, p, log_T, tid, nth);
+    int done = 0;
+    if constexpr (LOG_R >= 4) {
+#pragma unroll 1
+        for (; done + 4 <= LOG_R; done += 4) radix_step<LOG_R, 4>(x, tw, p, log_T, tid, nth, LOG_R - done - 4, done);
     }
+    constexpr int TAIL = LOG_R % 4;
+    if constexpr (TAIL > 0) radix_step<LOG_R, TAIL>(x, tw, p, log_T, tid, nth, 0, LOG_R - TAIL);
 }
 // position of frequency k after the in-place mixed-radix DIF: digits (radix 16, low digit first) reversed
 template <int LOG_R>
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams
     }
     __syncthreads();
     // ---- mixed-radix (16) DIF over r, butterflies in registers ----
-    radix_steps<LOG_R, 0>(x, tw, p, log_T, tid, nth);
+    radix_steps<LOG_R>(x, tw, p, log_T, tid, nth);
     // ---- store ----
     const gl scale(p.scale);
     for (int idx = tid; idx < total; idx += nth) {

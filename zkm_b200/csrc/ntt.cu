@@ -271,8 +271,8 @@ static void plan(int log_n, int& l1, int& l2, int& T) {
     if (log_n <= 12) { l1 = log_n; l2 = 0; T = (1 << 12) >> log_n; if (T > 16) T = 16; if (T < 1) T = 1; return; }
     l2 = log_n / 2; l1 = log_n - l2;
     int lmax = l1;   // l1 >= l2
-    T = (1 << 14) >> lmax;      // <= 16384 elements (131 KB + pad) per tile
-    if (T > 16) T = 16;
+    T = (1 << 13) >> lmax;      // <= 8192 elements (66 KB + pad) per tile: 3 CTAs per SM overlap their load/compute/store phases
+    if (T > 8) T = 8;
     if (T < 2) T = 2;
 }
 

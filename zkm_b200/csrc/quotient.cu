@@ -20,13 +20,17 @@ struct LdeRow {
     __device__ __forceinline__ gl operator[](int c) const { return gl(__ldg(base + (size_t)c * stride)); }
 };
 
+// Number of alpha-folds compiled into the kernels: StarkConfig::standard_fast_config has num_challenges = 2
+// (config.rs:17-29); every extra fold adds ~30 instructions to each of the hundreds of constraints.
+constexpr int QUOTIENT_ALPHAS = 2;
+
 struct DevConsumer {
-    gl alpha[MAX_CHALLENGES], acc[MAX_CHALLENGES];
+    gl alpha[QUOTIENT_ALPHAS], acc[QUOTIENT_ALPHAS];
     int na;
     gl z_last, l_first, l_last;
     __device__ __forceinline__ void constraint(gl c) {
 #pragma unroll
-        for (int a = 0; a < MAX_CHALLENGES; a++) if (a < na) acc[a] = acc[a] * alpha[a] + c;
+        for (int a = 0; a < QUOTIENT_ALPHAS; a++) acc[a] = acc[a] * alpha[a] + c;
     }
     __device__ __forceinline__ void constraint_transition(gl c) { constraint(c * z_last); }
     __device__ __forceinline__ void constraint_first_row(gl c) { constraint(c * l_first); }
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams q) {
     DevConsumer yc;
     yc.na = q.na;
 #pragma unroll
-    for (int a = 0; a < MAX_CHALLENGES; a++) { yc.alpha[a] = gl(q.alphas[a]); yc.acc[a] = gl::zero(); }
+    for (int a = 0; a < QUOTIENT_ALPHAS; a++) { yc.alpha[a] = gl(q.alphas[a]); yc.acc[a] = gl::zero(); }
     yc.z_last = x - gl(q.last);
     // L_first(x) = (x^n - 1) / (n (x - 1)),  L_last(x) = (x^n - 1) / (n (g x - 1))   (verifier.rs:347-354;
     // the reference prover tabulates the same two polynomials with an LDE of the selectors, prover.rs:677-681)
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QParams q) {
 
     gl zi(q.zh_inv[i & 1]);
 #pragma unroll
-    for (int a = 0; a < MAX_CHALLENGES; a++)
+    for (int a = 0; a < QUOTIENT_ALPHAS; a++)
         if (a < q.na) q.q[(size_t)a * 2 * n + i] = (yc.acc[a] * zi).v;
 }
 
@@ -182,7 +186,7 @@ static quotient_kernel_t quotient_kernel_for(int kind) {
 
 void compute_quotient_values(int kind, const DProgram& prog, const tables::TableLayout& L, const Batch& trace, const Batch& aux,
                              const AuxChallenges& ch, const u64* alphas, int num_alphas, u64* d_q, cudaStream_t s) {
-    ZKM_CHECK(num_alphas <= MAX_CHALLENGES, "too many challenges");
+    ZKM_CHECK(num_alphas >= 1 && num_alphas <= QUOTIENT_ALPHAS, "num_challenges above 2 is not supported by the quotient kernels");
     ZKM_CHECK(trace.rate_bits == 2 && aux.rate_bits == 2, "quotient kernel expects rate_bits = 2");
     ZKM_CHECK(trace.log_n == aux.log_n && trace.ncols == L.ncols && aux.ncols == L.num_aux(), "quotient: batch shape mismatch");
     int log_n = trace.log_n;

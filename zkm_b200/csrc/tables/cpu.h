@@ -53,18 +53,23 @@ constexpr int G_HASH_VALUE = GENERAL, G_KHASH_VALUE = GENERAL, G_SHASH_VALUE = G
 
 constexpr uint64_t GOLDILOCKS_INVERSE_2EXP32 = 18446744065119617026ull;      // jumps.rs:15
 constexpr uint64_t MIPSEBADF = 0x9;                                           // witness/operation.rs:98
+// 2^-i mod p, i = 0..32 (used to turn the O(32^2) bit recompositions of misc.rs into running sums)
+ZKM_DEF_CONST(CPU_INV2, 33, {1ULL, 9223372034707292161ULL, 13835058052060938241ULL, 16140901060737761281ULL, 17293822565076172801ULL, 17870283317245378561ULL, 18158513693329981441ULL, 18302628881372282881ULL, 18374686475393433601ULL, 18410715272404008961ULL, 18428729670909296641ULL, 18437736870161940481ULL, 18442240469788262401ULL, 18444492269601423361ULL, 18445618169508003841ULL, 18446181119461294081ULL, 18446462594437939201ULL, 18446603331926261761ULL, 18446673700670423041ULL, 18446708885042503681ULL, 18446726477228544001ULL, 18446735273321564161ULL, 18446739671368074241ULL, 18446741870391329281ULL, 18446742969902956801ULL, 18446743519658770561ULL, 18446743794536677441ULL, 18446743931975630881ULL, 18446744000695107601ULL, 18446744035054845961ULL, 18446744052234715141ULL, 18446744060824649731ULL, 18446744065119617026ULL})
 
 // util.rs:15-21 limb_from_bits_le over n consecutive columns
 template <class P, class V>
 ZKM_HD P bits_le(const V& lv, int start, int n) {
+    // Horner from the top bit: sum_i bit_i 2^i with two additions per bit instead of a field multiplication
+    // (the same field element; only the evaluation order differs)
     P s = P(0);
-    for (int i = 0; i < n; i++) s = s + lv[start + i] * P((uint64_t)1 << i);
+    ZKM_ROLLED
+    for (int i = n - 1; i >= 0; i--) s = s + s + lv[start + i];
     return s;
 }
 template <class P>
 ZKM_HD P limb_from(const P* bits, int n) {
     P s = P(0);
-    for (int i = 0; i < n; i++) s = s + bits[i] * P((uint64_t)1 << i);
+    for (int i = n - 1; i >= 0; i--) s = s + s + bits[i];
     return s;
 }
 
@@ -76,6 +81,7 @@ ZKM_HD void eval_bootstrap_kernel(const V& lv, const V& nv, YC& yc) {
     yc.constraint_last_row(local_is_bootstrap);
     const P delta = next_is_bootstrap - local_is_bootstrap;
     yc.constraint_transition(delta * (delta + P(1)));
+    ZKM_ROLLED
     for (int c = 0; c < NUM_GP_CHANNELS; c++) {
         P filter = local_is_bootstrap * lv[ch(c, CH_USED)];
         yc.constraint(filter * lv[ch(c, CH_ADDR_CONTEXT)]);
@@ -241,24 +247,21 @@ ZKM_HD void eval_membus(const V& lv, YC& yc) {
 struct BitRun { int start, count; };
 template <class P, class V>
 ZKM_HD P word_from_runs(const V& lv, const BitRun* runs, int nruns) {
-    P s = P(0);
-    int pos = 0;
-    for (int r = 0; r < nruns; r++) {
-        for (int i = 0; i < runs[r].count; i++) {
-            if (runs[r].start >= 0) s = s + lv[runs[r].start + i] * P((uint64_t)1 << (pos + i));
-        }
-        pos += runs[r].count;
+    P s = P(0);                                   // Horner from the top bit of the last run down to bit 0
+    for (int r = nruns - 1; r >= 0; r--) {
+        ZKM_ROLLED
+        for (int i = runs[r].count - 1; i >= 0; i--) s = s + s + lv[runs[r].start + i];
     }
     return s;
 }
 // bits[start .. start+n) sign-extended to 32 bits (memio.rs:59-67 sign_extend::<_, N>)
 template <class P, class V>
 ZKM_HD P sign_extended(const V& lv, int start, int n) {
+    // low n bits by Horner, plus the top bit replicated over bits n..31: top * (2^32 - 2^n)
     P s = P(0);
-    for (int i = 0; i < n; i++) s = s + lv[start + i] * P((uint64_t)1 << i);
-    P top = lv[start + n - 1];
-    for (int i = n; i < 32; i++) s = s + top * P((uint64_t)1 << i);
-    return s;
+    ZKM_ROLLED
+    for (int i = n - 1; i >= 0; i--) s = s + s + lv[start + i];
+    return s + lv[start + n - 1] * P(((uint64_t)1 << 32) - ((uint64_t)1 << n));
 }
 // memio.rs:24-32 load_offset: 16-bit immediate (func, shamt, rd bits) sign-extended
 template <class P, class V>
@@ -417,6 +420,7 @@ ZKM_HD void eval_count(const V& lv, YC& yc) {
     yc.constraint(filter * (lv[ch(1, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RD_BITS, 5)));
     const P rs = lv[ch(0, CH_VALUE)];
     const int BITS = G_IO_RS_LE;
+    ZKM_ROLLED
     for (int i = 0; i < 32; i++) { P bit = lv[BITS + i]; yc.constraint(filter * bit * (P(1) - bit)); }
     P sum = bits_le<P>(lv, BITS, 32);
     yc.constraint(filter_clz * (rs - sum));
@@ -424,8 +428,10 @@ ZKM_HD void eval_count(const V& lv, YC& yc) {
     const P rd = lv[ch(1, CH_VALUE)];
     int k = 0;                                             // walks rt_le (is_eq) and mem_le (inv) together
     yc.constraint(filter * lv[BITS + 31] * rd);
+    P partial = lv[BITS + 31];                             // sum_{k >= i} bit_k 2^(k-i), updated as bit_i + 2 * previous
+    ZKM_ROLLED
     for (int i = 30; i >= 0; i--) {
-        P partial = bits_le<P>(lv, BITS + i, 32 - i);
+        partial = lv[BITS + i] + partial + partial;
         P is_eq = lv[G_IO_RT_LE + k], inv = lv[G_IO_MEM_LE + k];
         k++;
         P diff = partial - P(1);
@@ -523,17 +529,16 @@ ZKM_HD void eval_bits(const V& lv, YC& yc) {
     yc.constraint(filter * (lv[ch(1, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RD_BITS, 5)));
     const P rt = lv[ch(0, CH_VALUE)];
     const int B = G_IO_RT_LE;
+    ZKM_ROLLED
     for (int i = 0; i < 32; i++) { P bit = lv[B + i]; yc.constraint(filter * bit * (P(1) - bit)); }
     yc.constraint(filter * (rt - bits_le<P>(lv, B, 32)));
     const P rd = lv[ch(1, CH_VALUE)];
     {   // seb: bits 0..6 then bit 7 replicated
-        P s = bits_le<P>(lv, B, 7);
-        for (int i = 7; i < 32; i++) s = s + lv[B + 7] * P((uint64_t)1 << i);
+        P s = bits_le<P>(lv, B, 7) + lv[B + 7] * P(((uint64_t)1 << 32) - ((uint64_t)1 << 7));
         yc.constraint(filter_seb * (rd - s));
     }
     {   // seh
-        P s = bits_le<P>(lv, B, 15);
-        for (int i = 15; i < 32; i++) s = s + lv[B + 15] * P((uint64_t)1 << i);
+        P s = bits_le<P>(lv, B, 15) + lv[B + 15] * P(((uint64_t)1 << 32) - ((uint64_t)1 << 15));
         yc.constraint(filter_seh * (rd - s));
     }
     {   // wsbh
@@ -586,9 +591,11 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
         const P auxm = lv[G_MISC_AUXM], auxl = lv[G_MISC_AUXL], auxs = lv[G_MISC_AUXS];
         const P rd_result = lv[ch(1, CH_VALUE)];
         yc.constraint(filter * (rd_result * auxs + auxl - auxm));
+        P mpartial = P(0), lpartial = P(0);                 // sum_{j <= i} / sum_{j < i} rs_bits[j] 2^j, as running sums
+        ZKM_ROLLED
         for (int i = 0; i < 32; i++) {
-            P mpartial = bits_le<P>(lv, G_MISC_RS_BITS, i + 1);
-            P lpartial = i != 0 ? bits_le<P>(lv, G_MISC_RS_BITS, i) : P(0);
+            lpartial = mpartial;
+            mpartial = mpartial + lv[G_MISC_RS_BITS + i] * P((uint64_t)1 << i);
             P is_msb = lv[G_MISC_IS_MSB + i], is_lsb = lv[G_MISC_IS_LSB + i];
             P cur_index = P((uint64_t)i), cur_mul = P((uint64_t)1 << i);
             yc.constraint(filter * is_msb * (msb - cur_index));
@@ -604,9 +611,14 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
         yc.constraint(filter * (lv[ch(0, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RT_BITS, 5)));
         const P sa = bits_le<P>(lv, SHAMT_BITS, 5);
         const P rd_result = lv[ch(1, CH_VALUE)];
+        // rd_val_i = (bits >> i) | (low i bits << (32 - i)) = hi_i + lo_i * 2^(32-i), hi/lo as running sums
+        const P full = bits_le<P>(lv, G_MISC_RS_BITS, 32);
+        P lo_run = P(0);
+        ZKM_ROLLED
         for (int i = 0; i < 32; i++) {
-            const BitRun r[2] = {{G_MISC_RS_BITS + i, 32 - i}, {G_MISC_RS_BITS, i}};
-            P rd_val = word_from_runs<P>(lv, r, 2);
+            // hi_i = sum_{k >= i} b_k 2^(k-i) = (full - lo_i) / 2^i   (exact field identity)
+            P rd_val = (full - lo_run) * P(ZKM_K(CPU_INV2)[i]) + lo_run * P((uint64_t)1 << (32 - i));
+            lo_run = lo_run + lv[G_MISC_RS_BITS + i] * P((uint64_t)1 << i);
             P is_sa = lv[G_MISC_IS_LSB + i];
             yc.constraint(filter * is_sa * (sa - P((uint64_t)i)));
             yc.constraint(filter * is_sa * (rd_result - rd_val));
@@ -623,13 +635,15 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
         const P auxm = lv[G_MISC_AUXM], auxl = lv[G_MISC_AUXL], auxs = lv[G_MISC_AUXS];
         const P rd_result = lv[ch(2, CH_VALUE)];
         yc.constraint(filter * (rd_result - auxm - auxl * auxs));
+        P insert_val = P(0);
+        ZKM_ROLLED
         for (int i = 0; i < 32; i++) {
             P is_msb = lv[G_MISC_IS_MSB + i], is_lsb = lv[G_MISC_IS_LSB + i];
             P cur_index = P((uint64_t)i), cur_mul = P((uint64_t)1 << i);
             yc.constraint(filter * is_lsb * (lsb - cur_index));
             yc.constraint(filter * is_lsb * (auxs - cur_mul));
             yc.constraint(filter * is_msb * (msb - lsb - cur_index));
-            P insert_val = bits_le<P>(lv, G_MISC_RS_BITS, i + 1);
+            insert_val = insert_val + lv[G_MISC_RS_BITS + i] * P((uint64_t)1 << i);
             yc.constraint(filter * is_msb * (auxl - insert_val));
         }
     }

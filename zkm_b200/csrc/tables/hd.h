@@ -27,3 +27,12 @@
 #else
 #define ZKM_K(name) H_##name
 #endif
+
+// Loops over bits / limbs / channels in the constraint templates are kept rolled on the device: the quotient
+// kernels are straight-line code executed once per thread, so their cost is instruction fetch, i.e. code
+// size (the fully unrolled Cpu kernel was 87 000 SASS instructions).
+#ifdef __CUDACC__
+#define ZKM_ROLLED _Pragma("unroll 1")
+#else
+#define ZKM_ROLLED
+#endif

@@ -24,13 +24,13 @@ ZKM_HD void eval(const V& lv, const V& /*nv*/, YC& yc) {
         P bit = lv[i];
         yc.constraint(bit * (bit - P(1)));
     }
+    // sum_i bit_i 2^i by Horner from the top bit (same field elements as the reference's weighted sums)
     P x = P(0), y = P(0), x_land_y = P(0);
-    for (int i = 0; i < VAL_BITS; i++) {
+    for (int i = VAL_BITS - 1; i >= 0; i--) {
         P xb = lv[INPUT0 + i], yb = lv[INPUT1 + i];
-        P w = P((uint64_t)1 << i);
-        x = x + xb * w;
-        y = y + yb * w;
-        x_land_y = x_land_y + xb * yb * w;
+        x = x + x + xb;
+        y = y + y + yb;
+        x_land_y = x_land_y + x_land_y + xb * yb;
     }
     P x_op_y = sum_coeff * (x + y) + and_coeff * x_land_y + not_coeff * P(0xFFFFFFFFull);
     yc.constraint(lv[RESULT] - x_op_y);

@@ -155,6 +155,7 @@ struct Consumer {
     void constraint_transition(P c) { constraint(c * z_last); }
     void constraint_first_row(P c) { constraint(c * l_first); }
     void constraint_last_row(P c) { constraint(c * l_last); }
+    void checkpoint() {}            // device consumers re-converge the CTA here (instruction-cache sharing); no-op on the CPU
 };
 
 template <class P>

@@ -24,14 +24,29 @@ struct LdeRow {
 // (config.rs:17-29); every extra fold adds ~30 instructions to each of the hundreds of constraints.
 constexpr int QUOTIENT_ALPHAS = 2;
 
+// The alpha-fold acc <- acc * alpha + c runs once per constraint (hundreds of times per point).  It is a
+// NON-inlined function so that its ~55 instructions exist once in the instruction cache instead of once per
+// constraint (the straight-line constraint code is instruction-fetch bound); the alphas live in constant memory.
+__constant__ u64 c_quotient_alpha[QUOTIENT_ALPHAS];
+struct FoldPair { u64 a0, a1; };
+__device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
+    FoldPair r;
+    r.a0 = (gl(a0) * gl(c_quotient_alpha[0]) + gl(c)).v;
+    r.a1 = (gl(a1) * gl(c_quotient_alpha[1]) + gl(c)).v;
+    return r;
+}
+
 struct DevConsumer {
     gl alpha[QUOTIENT_ALPHAS], acc[QUOTIENT_ALPHAS];
     int na;
     gl z_last, l_first, l_last;
     __device__ __forceinline__ void constraint(gl c) {
-#pragma unroll
-        for (int a = 0; a < QUOTIENT_ALPHAS; a++) acc[a] = acc[a] * alpha[a] + c;
+        FoldPair r = quotient_fold(acc[0].v, acc[1].v, c.v);
+        acc[0] = gl(r.a0); acc[1] = gl(r.a1);
     }
+    // Re-converges the CTA: the constraint code is straight-line and instruction-fetch bound (ncu: "no instruction"
+    // is the top stall), so keeping all warps of a CTA inside the same code window lets them share fetched lines.
+    __device__ __forceinline__ void checkpoint() { __syncthreads(); }
     __device__ __forceinline__ void constraint_transition(gl c) { constraint(c * z_last); }
     __device__ __forceinline__ void constraint_first_row(gl c) { constraint(c * l_first); }
     __device__ __forceinline__ void constraint_last_row(gl c) { constraint(c * l_last); }
@@ -138,10 +153,9 @@ __device__ __forceinline__ gl gl_inv_q(gl x) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) quotient_kernel(QParams q) {
+__global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
     const size_t n = (size_t)1 << q.log_n;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n) return;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the 2n points exactly (no early exit: checkpoints)
     const size_t half = t >> q.log_n, idx = t & (n - 1);
     const size_t i = 2 * idx + half;                        // index in the quotient domain 7*H_{2n}
     const size_t pos = (2 * half) * n + idx, pos_next = (2 * half) * n + ((idx + 1) & (n - 1));
@@ -207,9 +221,15 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     gl g = gl_root_of_unity(log_n);
     q.g = g.v; q.last = gl_inv(g).v; q.n_inv = gl_inv(gl((u64)n)).v;
     q.q = d_q;
+    {
+        u64 ha[QUOTIENT_ALPHAS] = {0, 0};
+        for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
+        ZKM_CUDA(cudaMemcpyToSymbolAsync(c_quotient_alpha, ha, sizeof(ha), 0, cudaMemcpyHostToDevice, s));
+    }
     quotient_kernel_t k = quotient_kernel_for(kind);
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
-    k<<<(unsigned)((2 * n + 127) / 128), 128, 0, s>>>(q);
+    const unsigned threads = 2 * n >= 512 ? 512 : (unsigned)(2 * n);
+    k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
     ZKM_LAUNCHED();
     ZKM_CUDA(cudaStreamSynchronize(s));                      // keeps `tab` alive until the kernel has run
 }

@@ -312,25 +312,32 @@ ZKM_HD void eval(const V& lv, const V& nv, YC& yc) {
     read2<P>(lv, OUTPUT_REGISTER, out); read2<P>(lv, AUX_INPUT_REGISTER_0, aux0);
     // mul
     eval_mul<P, V, YC>(lv, lv[IS_MUL], in0, in1, yc);
+    yc.checkpoint();
     // mult / multu
     eval_mult<P, V, YC>(lv, yc);
+    yc.checkpoint();
     // addcy (addcy.rs:142-160)
     eval_addcy<P, YC>(yc, lv[IS_ADD], in0, in1, out, aux0, false);
     eval_addcy<P, YC>(yc, lv[IS_SUB], in1, out, in0, aux0, false);
     eval_addcy<P, YC>(yc, lv[IS_ADDI], in0, in1, out, aux0, false);
     eval_addcy<P, YC>(yc, lv[IS_ADDIU], in0, in1, out, aux0, false);
+    yc.checkpoint();
     // slt
     eval_slt<P, V, YC>(lv, yc);
     // lui (lui.rs:59-71): a multiplication
     eval_mul<P, V, YC>(lv, lv[IS_LUI], in0, in1, yc);
     // divu then div (div.rs:381-401)
     eval_div_helper<P, V, YC>(lv, nv, yc, lv[IS_DIVU], INPUT_REGISTER_0, INPUT_REGISTER_1, OUTPUT_REGISTER, AUX_INPUT_REGISTER_0);
+    yc.checkpoint();
     eval_div_signed<P, V, YC>(lv, nv, yc);
+    yc.checkpoint();
     // sll (shift.rs:128-139) then srl (:141-157)
     eval_mul<P, V, YC>(lv, lv[IS_SLL] + lv[IS_SLLV], in1, in2, yc);
     eval_div_helper<P, V, YC>(lv, nv, yc, lv[IS_SRL] + lv[IS_SRLV], INPUT_REGISTER_1, INPUT_REGISTER_2, OUTPUT_REGISTER, AUX_INPUT_REGISTER_0);
+    yc.checkpoint();
     // sra
     eval_sra<P, V, YC>(lv, nv, yc);
+    yc.checkpoint();
     // lo_hi (lo_hi.rs:25-39)
     const P f = lv[IS_MFHI] + lv[IS_MTHI] + lv[IS_MFLO] + lv[IS_MTLO];
     for (int i = 0; i < N_LIMBS; i++) yc.constraint(f * (in0[i] - out[i]));

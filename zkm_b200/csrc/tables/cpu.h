@@ -336,6 +336,7 @@ ZKM_HD void eval_load(const V& lv, YC& yc) {
         P mem_val_0 = bits_le<P>(lv, MEM + 16, 16), mem_val_1 = bits_le<P>(lv, MEM, 16);
         enforce_half_word<P, YC>(yc, lv[MEMIO_IS_LHU], rs1, mem, mem_val_1, mem_val_0);
     }
+    yc.checkpoint();
     {   // LWR
         const BitRun r00[2] = {{MEM + 24, 8}, {RT + 8, 24}}, r10[2] = {{MEM + 16, 16}, {RT + 16, 16}}, r01[2] = {{MEM + 8, 24}, {RT + 24, 8}},
                      r11[1] = {{MEM, 32}};
@@ -343,6 +344,7 @@ ZKM_HD void eval_load(const V& lv, YC& yc) {
                                word_from_runs<P>(lv, r01, 2), word_from_runs<P>(lv, r11, 1));
     }
     yc.constraint(lv[MEMIO_IS_LL] * (mem - bits_le<P>(lv, MEM, 32)));
+    yc.checkpoint();
     {   // LB: sign-extended bytes
         enforce_byte<P, V, YC>(yc, lv, lv[MEMIO_IS_LB], rs0, rs1, mem, sign_extended<P>(lv, MEM + 24, 8), sign_extended<P>(lv, MEM + 16, 8),
                                sign_extended<P>(lv, MEM + 8, 8), sign_extended<P>(lv, MEM, 8));
@@ -367,6 +369,7 @@ ZKM_HD void eval_store(const V& lv, YC& yc) {
         const BitRun r0[2] = {{MEM, 16}, {RT, 16}}, r1[2] = {{RT, 16}, {MEM + 16, 16}};
         enforce_half_word<P, YC>(yc, lv[MEMIO_IS_SH], rs1, mem, word_from_runs<P>(lv, r1, 2), word_from_runs<P>(lv, r0, 2));
     }
+    yc.checkpoint();
     {   // SWL
         const BitRun r00[1] = {{RT, 32}}, r10[2] = {{RT + 8, 24}, {MEM + 24, 8}}, r01[2] = {{RT + 16, 16}, {MEM + 16, 16}},
                      r11[2] = {{RT + 24, 8}, {MEM + 8, 24}};
@@ -374,6 +377,7 @@ ZKM_HD void eval_store(const V& lv, YC& yc) {
                                word_from_runs<P>(lv, r01, 2), word_from_runs<P>(lv, r11, 2));
     }
     yc.constraint(lv[MEMIO_IS_SW] * (mem - bits_le<P>(lv, RT, 32)));
+    yc.checkpoint();
     {   // SWR
         const BitRun r00[2] = {{MEM, 24}, {RT, 8}}, r10[2] = {{MEM, 16}, {RT, 16}}, r01[2] = {{MEM, 8}, {RT, 24}}, r11[1] = {{RT, 32}};
         enforce_byte<P, V, YC>(yc, lv, lv[MEMIO_IS_SWR], rs0, rs1, mem, word_from_runs<P>(lv, r00, 2), word_from_runs<P>(lv, r10, 2),
@@ -563,6 +567,7 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
         yc.constraint(filter * rd_eq_29 * (rt_val - local_user));
         yc.constraint(filter * (P(1) - rd_eq_29 - rd_eq_0) * rt_val);
     }
+    yc.checkpoint();
     {   // condmov
         const P rs = lv[ch(0, CH_VALUE)], rt = lv[ch(1, CH_VALUE)], rd = lv[ch(2, CH_VALUE)], out = lv[ch(3, CH_VALUE)], mov = lv[ch(4, CH_VALUE)];
         const P is_movn = lv[OP_MOVN_OP], is_movz = lv[OP_MOVZ_OP];
@@ -581,6 +586,7 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
         const P is_ne = (lv[ch(0, CH_VALUE)] - lv[ch(1, CH_VALUE)]) * lv[G_LOGIC_DIFF_PINV];
         yc.constraint(filter * (P(1) - is_ne));
     }
+    yc.checkpoint();
     {   // extract
         const P filter = lv[OP_EXT];
         yc.constraint(filter * (lv[ch(1, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RT_BITS, 5)));
@@ -605,6 +611,7 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
             yc.constraint(filter * is_lsb * (auxs - cur_mul));
         }
     }
+    yc.checkpoint();
     {   // ror
         const P filter = lv[OP_ROR];
         yc.constraint(filter * (lv[ch(1, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RD_BITS, 5)));
@@ -624,6 +631,7 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
             yc.constraint(filter * is_sa * (rd_result - rd_val));
         }
     }
+    yc.checkpoint();
     {   // insert
         const P filter = lv[OP_INS];
         const P rt_src = bits_le<P>(lv, RT_BITS, 5);
@@ -647,6 +655,7 @@ ZKM_HD void eval_misc(const V& lv, YC& yc) {
             yc.constraint(filter * is_msb * (auxl - insert_val));
         }
     }
+    yc.checkpoint();
     {   // maddu
         const P filter = lv[OP_MADDU];
         yc.constraint(filter * (lv[ch(0, CH_ADDR_VIRTUAL)] - bits_le<P>(lv, RS_BITS, 5)));
@@ -672,16 +681,25 @@ template <class P, class V, class YC>
 ZKM_HD void eval(const V& lv, const V& nv, YC& yc) {
     eval_bootstrap_kernel<P, V, YC>(lv, nv, yc);
     eval_decode<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_jump_jumpi<P, V, YC>(lv, nv, yc);
+    yc.checkpoint();
     eval_branch<P, V, YC>(lv, nv, yc);
     eval_membus<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_load<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_store<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_shift<P, V, YC>(lv, yc);
     eval_count<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_syscall<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_bits<P, V, YC>(lv, yc);
+    yc.checkpoint();
     eval_misc<P, V, YC>(lv, yc);
+    yc.checkpoint();
 }
 
 // ---- CTL selectors (cpu_stark.rs:25-244)

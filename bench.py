@@ -260,6 +260,63 @@ def synthetic_traces_host(log_heights, seed=0x5EED000000000000):
     return out
 
 
+def run_n22(args):
+    """BASELINE config #3: 2^22-row columns, NTT + Merkle only (PolynomialBatch::from_values), C in {1, 13, 54, 259}.
+    Prints one JSON line per C with the NTT figure BASELINE asks for: 48*n*C algorithmic bytes (read values,
+    write coefficients, write the 4n LDE) over the NTT kernels' device time, against the measured HBM peak."""
+    import torch
+    from zkm_b200 import lib as zl
+    lib = zl.init(0)
+    peak, peak_kind = peaks()
+    log_n = int(args.workload[1:])
+    n = 1 << log_n
+    for ncols in (1, 13, 54, 259):
+        buf = torch.empty(ncols * n, dtype=torch.int64, device="cuda")
+        err = C.c_void_p()
+        zl.check(lib, lib.zkm_b200_synth_columns_device(buf.data_ptr(), ncols, log_n, 0x5EED000000000000 | ncols, C.byref(err)), err)
+        cap = np.zeros(64, dtype=np.uint64)
+
+        def step():
+            h = C.c_void_p()
+            zl.check(lib, lib.zkm_b200_commit_values_device(buf.data_ptr(), ncols, log_n, 2, 4, C.byref(h), zl.u64ptr(cap), C.byref(err)), err)
+            lib.zkm_b200_batch_free(h)
+
+        for _ in range(max(3, args.warmup)):
+            step()
+        lib.zkm_b200_profile_enable(1)
+        zl.check(lib, lib.zkm_b200_profile_reset(C.byref(err)), err)
+        ms = C.c_double()
+        zl.check(lib, lib.zkm_b200_timer_start(C.byref(err)), err)
+        for _ in range(args.steps):
+            step()
+        zl.check(lib, lib.zkm_b200_timer_stop(C.byref(ms), C.byref(err)), err)
+        fam = {}
+        for name in ("ntt_pass", "leaf_hash", "merkle_levels"):
+            m, la, by = C.c_double(), C.c_uint64(), C.c_double()
+            rc = lib.zkm_b200_profile_get(name.encode(), C.byref(m), C.byref(la), C.byref(by), C.byref(err))
+            if rc == 0:
+                fam[name] = {"ms_per_step": m.value / args.steps, "launches_per_step": la.value / args.steps}
+            else:
+                lib.zkm_b200_free_string(err)
+        lib.zkm_b200_profile_enable(0)
+        t_ntt = fam.get("ntt_pass", {"ms_per_step": 0})["ms_per_step"]
+        alg = 48.0 * n * ncols
+        ach = alg / (t_ntt * 1e-3) / 1e9 if t_ntt else 0.0
+        perms = 4 * n * ((ncols + 7) // 8 if ncols > 4 else 0) + 4 * n - 16
+        t_hash = sum(fam.get(k, {"ms_per_step": 0})["ms_per_step"] for k in ("leaf_hash", "merkle_levels"))
+        print(json.dumps({"metric": f"NTT GB/s (iNTT + coset LDE x4 of {ncols} columns x 2^{log_n}; 48*n*C algorithmic bytes)", "value": ach,
+                          "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+                          "ms_per_step": ms.value / args.steps, "higher_is_better": True, "dtype": "u64 (Goldilocks)", "data": "synthetic",
+                          "config": {"workload": args.workload, "columns": ncols, "stages": "a1+a2 (from_values: NTT + Poseidon Merkle cap)"},
+                          "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                       "frac": ach / peak, "peak_kind": peak_kind, "traffic": None,
+                                       "pass_traffic_GBps": 160.0 * n * ncols / (t_ntt * 1e-3) / 1e9 if t_ntt else 0.0},
+                          "poseidon": {"permutations": perms, "Gperm_per_s": perms / (t_hash * 1e-3) / 1e9 if t_hash else 0.0},
+                          "kernel_families": fam}), flush=True)
+        del buf
+        torch.cuda.empty_cache()
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The Rust reference cannot be
     built in this image (no cargo; plonky2 un-vendored — DESIGN.md), so this times the restated C++
@@ -296,6 +353,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload.startswith("N"):
+        return run_n22(args)
 
     import torch
     import torch.distributed as dist

@@ -40,7 +40,7 @@ void orc_ext_inv(const uint64_t* a, uint64_t* out) {
 void orc_poseidon_permute(uint64_t* st, int fast) {
     PState s;
     for (int i = 0; i < 12; i++) s[i] = Fp(st[i]);
-    if (fast) poseidon_fast(s); else poseidon_naive(s);
+    if (fast == 2) poseidon_opt(s); else if (fast) poseidon_fast(s); else poseidon_naive(s);
     for (int i = 0; i < 12; i++) st[i] = s[i].v;
 }
 void orc_poseidon_permute_many(uint64_t* st, size_t count) {

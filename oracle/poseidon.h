@@ -101,7 +101,52 @@ static inline void poseidon_fast(PState& s) {
     }
 }
 
-static inline void poseidon(PState& s) { poseidon_naive(s); }
+// Optimised CPU schedule used for everything but the cross-checks (tests assert naive == fast == opt ==
+// Appendix D): the same permutation with (i) the MDS row sums taken over 32-bit halves in u64 accumulators
+// (the circulant entries are < 64, so no 128-bit arithmetic and the loops auto-vectorise), one reduction per
+// output, and (ii) lazily reduced S-box products.  This is the CPU arm's hash; a scalar Rust/plonky2 build
+// uses the same two ideas (plonky2 hash/poseidon_goldilocks.rs).
+static inline void mds_layer_opt(u64* s) {
+    static const u64 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    u64 lo[24], hi[24];
+    for (int i = 0; i < 12; i++) { lo[i] = lo[i + 12] = s[i] & 0xFFFFFFFFULL; hi[i] = hi[i + 12] = s[i] >> 32; }
+    u64 al[12], ah[12];
+    for (int r = 0; r < 12; r++) {
+        u64 a = 0, b = 0;
+        for (int i = 0; i < 12; i++) { a += lo[i + r] * C[i]; b += hi[i + r] * C[i]; }
+        al[r] = a; ah[r] = b;
+    }
+    al[0] += lo[0] * 8; ah[0] += hi[0] * 8;
+    for (int r = 0; r < 12; r++) {
+        u128 v = (u128)al[r] + ((u128)ah[r] << 32);
+        s[r] = gl_reduce128(v);
+    }
+}
+static inline u64 mulred(u64 a, u64 b) { return gl_reduce128((u128)a * b); }
+static inline u64 sbox7_opt(u64 x) {
+    u64 x2 = mulred(x, x), x3 = mulred(x2, x), x4 = mulred(x2, x2);
+    return mulred(x3, x4);
+}
+static inline void poseidon_opt(PState& st) {
+    u64 s[12];
+    for (int i = 0; i < 12; i++) s[i] = st[i].v;
+    int rc = 0;
+    for (int r = 0; r < 30; r++) {
+        const bool full = r < 4 || r >= 26;
+        for (int i = 0; i < 12; i++) {
+            u64 t = s[i] + POSEIDON_ALL_ROUND_CONSTANTS[rc + i];          // both < p: at most one wrap
+            if (t < s[i] || t >= GL_P) t -= GL_P;
+            s[i] = t;
+        }
+        rc += 12;
+        if (full) { for (int i = 0; i < 12; i++) s[i] = sbox7_opt(s[i]); }
+        else s[0] = sbox7_opt(s[0]);
+        mds_layer_opt(s);
+    }
+    for (int i = 0; i < 12; i++) st[i].v = s[i];
+}
+
+static inline void poseidon(PState& s) { poseidon_opt(s); }
 
 // plonky2 hash_n_to_m_no_pad with m = 4: overwrite-mode sponge, rate 8 (Appendix A.4).
 static inline Digest hash_no_pad(const Fp* in, size_t n) {

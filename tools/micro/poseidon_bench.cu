@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(128, MINB) k_perm_vx(const u64* __restrict__ i
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = in[k * count + i];
     for (int r = 0; r < reps; r++) {
-        if (V == 4) poseidon_permute_v4(s); else poseidon_permute_v6(s);
+        if (V == 4) poseidon_permute_v4(s);
+        else if (V == 6) poseidon_permute_v6(s);
+        else if (V == 8) poseidon_permute_v8(s);
+        else if (V == 9) poseidon_permute_v9_t<true>(s);
+        else poseidon_permute_v9_t<false>(s);
     }
 #pragma unroll
     for (int k = 0; k < 12; k++) out[k * count + i] = s[k];
@@ -148,6 +152,13 @@ int main() {
     timeit("v4 single-loop lb(128,8)", [&] { k_perm_vx<4, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v6 rolled sbox lb(128,6)", [&] { k_perm_vx<6, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v6");
     timeit("v6 rolled sbox lb(128,8)", [&] { k_perm_vx<6, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v8 merged consts lb(128,6)", [&] { k_perm_vx<8, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v8");
+    timeit("v9 freq-mds paired lb(128,6)", [&] { k_perm_vx<9, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9");
+    timeit("v9 freq-mds paired lb(128,5)", [&] { k_perm_vx<9, 5><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v9 freq-mds paired lb(128,4)", [&] { k_perm_vx<9, 4><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v9 freq-mds paired lb(128,8)", [&] { k_perm_vx<9, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v10 freq-mds unpaired lb(128,6)", [&] { k_perm_vx<10, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v10");
+    timeit("v10 freq-mds unpaired lb(128,5)", [&] { k_perm_vx<10, 5><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v2 x2 states/thread", [&] { k_perm_x2<<<g / 2, 128>>>(din, dout, count, reps); }, count, reps);
 #endif
     return 0;

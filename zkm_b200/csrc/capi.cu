@@ -428,7 +428,7 @@ __global__ void poseidon_states_kernel(u64* st, size_t count) {
     u64 s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = st[i * 12 + k];
-    poseidon_permute_v8(s);
+    poseidon_permute_dev(s);
 #pragma unroll
     for (int k = 0; k < 12; k++) st[i * 12 + k] = s[k];
 }

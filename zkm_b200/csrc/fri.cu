@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) fri_pow_kernel(PowParams p, unsigned long
     for (int i = 0; i < 12; i++) s[i] = p.state[i];
 #pragma unroll
     for (int i = 0; i < 12; i++) if (i == p.pos) s[i] = w;
-    poseidon_permute_v8(s);
+    poseidon_permute_dev(s);
     int lz = s[7] ? __clzll((long long)s[7]) : 64;
     if (lz >= p.min_lz) atomicMin(best, (unsigned long long)w);
 }

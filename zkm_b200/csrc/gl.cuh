@@ -31,16 +31,32 @@ struct gl {
     static ZKM_HD gl one() { return gl(1); }
 };
 
+// ZKM_GLADD selects the device add/sub: 0 = compare/select C code, 1 = borrow-chain PTX (a - b: a borrow is fixed by
+// subtracting 2^32 - 1, i.e. adding p mod 2^64; a + b = a - (p - b)).
+#ifndef ZKM_GLADD
+#define ZKM_GLADD 1
+#endif
+ZKM_HD gl operator-(gl a, gl b) {
+#if defined(__CUDA_ARCH__) && ZKM_GLADD == 1
+    u32 a0 = (u32)a.v, a1 = (u32)(a.v >> 32), b0 = (u32)b.v, b1 = (u32)(b.v >> 32), o0, o1;
+    asm("{\n\t.reg .u32 t0,t1,m;\n\tsub.cc.u32 t0, %2, %4;\n\tsubc.cc.u32 t1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, t0, m;\n\tsubc.u32 %1, t1, 0;\n\t}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl((u64)o0 | ((u64)o1 << 32));
+#else
+    u64 d = a.v - b.v;
+    if (a.v < b.v) d += GL_P;
+    return gl(d);
+#endif
+}
 ZKM_HD gl operator+(gl a, gl b) {
+#if defined(__CUDA_ARCH__) && ZKM_GLADD == 1
+    return a - gl(GL_P - b.v);      // p - b in (0, p]: the borrow chain treats p like 0
+#else
     u64 s = a.v + b.v;
     // a,b < p: true sum < 2p; wrapped iff s < a.v
     if (s < a.v || s >= GL_P) s -= GL_P;
     return gl(s);
-}
-ZKM_HD gl operator-(gl a, gl b) {
-    u64 d = a.v - b.v;
-    if (a.v < b.v) d += GL_P;
-    return gl(d);
+#endif
 }
 ZKM_HD gl operator-(gl a) { return gl(a.v ? GL_P - a.v : 0); }
 
@@ -64,8 +80,15 @@ ZKM_HD u64 gl_reduce96(u64 lo, u32 hi32) {
     return r;
 }
 
+// ZKM_GLMUL selects the device multiply: 0 = PTX product + PTX folding, 1 = compiler product + 128-bit-sum folding,
+// 2 = compiler product + compare/select folding, 3 = compiler product + PTX folding.  The kernels built on this are bound by
+// the ALU pipe (IADD3/LOP3/SEL, ncu: 72-78 % vs 15 % on the FMA pipe), so what counts is how much of the carry handling the
+// compiler can place on the FMA pipe (IMAD.WIDE with carry-out, IMAD.X), not the instruction total.
+#ifndef ZKM_GLMUL
+#define ZKM_GLMUL 3
+#endif
 ZKM_HD gl operator*(gl a, gl b) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && ZKM_GLMUL == 0
     // 4 IMAD.WIDE + two IADD3 carry chains (product, then 2^64 = 2^32 - 1 / 2^96 = -1 folding); see
     // poseidon_v2.cuh p2_mul for the derivation.  ~20 SASS instructions instead of ~28.
     u32 a0 = (u32)a.v, a1 = (u32)(a.v >> 32), b0 = (u32)b.v, b1 = (u32)(b.v >> 32);
@@ -82,6 +105,32 @@ ZKM_HD gl operator*(gl a, gl b) {
         "sub.u32 m, 0, c;\n\t"
         "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
         : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    u64 r = (u64)o0 | ((u64)o1 << 32);
+    return gl(r >= GL_P ? r - GL_P : r);
+#elif defined(__CUDA_ARCH__) && ZKM_GLMUL == 1
+    // x = lo + r2 * (2^32 - 1) - r3 computed as the 66-bit sum s = lo + r2 * EPS + (EPS - r3) = x + 2^64 (mod p);
+    // s = sl + sh * 2^64 with sh in {0, 1, 2}  =>  x = sl + (sh - 1) * EPS, which neither wraps nor goes negative.
+    unsigned __int128 pr = (unsigned __int128)a.v * b.v;
+    u64 lo = (u64)pr, hi = (u64)(pr >> 64);
+    u32 r2 = (u32)hi, r3 = (u32)(hi >> 32);
+    unsigned __int128 sm = (unsigned __int128)lo + (unsigned __int128)((u64)r2 * GL_EPS) + (unsigned __int128)(GL_EPS - r3);
+    u64 sl = (u64)sm;
+    long long sh = (long long)(u64)(sm >> 64) - 1;
+    u64 r = sl + (((u64)sh) << 32) - (u64)sh;
+    return gl(r >= GL_P ? r - GL_P : r);
+#elif defined(__CUDA_ARCH__) && ZKM_GLMUL == 3
+    unsigned __int128 pr = (unsigned __int128)a.v * b.v;
+    u64 lo = (u64)pr, hi = (u64)(pr >> 64);
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32);
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 s0,s1,t0,tt1,b,c,m;\n\t"
+        "add.cc.u32 s0, %4, %5;\n\taddc.u32 s1, 0, 0;\n\t"
+        "sub.cc.u32 t0, %2, s0;\n\tsubc.cc.u32 tt1, %3, s1;\n\tsubc.u32 b, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
+        "add.cc.u32 tt1, tt1, %4;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
     u64 r = (u64)o0 | ((u64)o1 << 32);
     return gl(r >= GL_P ? r - GL_P : r);
 #else

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128, 6) lde_leaf_hash_kernel(const u64* __rest
         for (int c = 0; c < ncols; c += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) if (c + k < ncols) s[k] = __ldg(col + (size_t)(c + k) * cs);
-            poseidon_permute_v8(s);
+            poseidon_permute_dev(s);
         }
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + (size_t)leaf * 4);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 6) rows_leaf_hash_kernel(const u64* __res
         for (int c = 0; c < width; c += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) if (c + k < width) s[k] = row[c + k];
-            poseidon_permute_v8(s);
+            poseidon_permute_dev(s);
         }
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(dig + leaf * 4);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128, 6) merkle_level_kernel(const u64* __restr
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
     ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
     u64 s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
-    poseidon_permute_v8(s);
+    poseidon_permute_dev(s);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(parent + i * 4);
     o[0] = make_ulonglong2(s[0], s[1]);
     o[1] = make_ulonglong2(s[2], s[3]);

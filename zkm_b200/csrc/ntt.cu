@@ -58,7 +58,7 @@ struct NttPassParams {
 constexpr int NTT_MAX_THREADS = 1024;
 
 // a * b mod p (canonical) with the hand-scheduled product/reduction of poseidon_v2.cuh
-__device__ __forceinline__ gl fmul(gl a, gl b) { return gl(lz_canon(p2_mul(a.v, b.v))); }
+__device__ __forceinline__ gl fmul(gl a, gl b) { return a * b; }
 
 // Size-2^B DIF network on registers; v[j] ends up holding frequency bitrev_B(j).  w16[e] = w_16^e.
 template <int B>

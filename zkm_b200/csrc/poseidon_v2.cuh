@@ -202,6 +202,142 @@ __device__ __forceinline__ void poseidon_permute_v8(u64* s) {
     for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
 }
 
+// ---- v9: fewer instructions per permutation (the kernels are issue-slot bound, ncu: profiles/r1_*):
+//  (a) the 128-bit product comes from the compiler's own 64x64 multiply (IMAD.WIDE.U32 with carry-out predicate +
+//      IMAD.WIDE.U32.X carry-in: 4 IMAD + 2 IADD3, not reachable from PTX mad/add.cc), the 2^64 = 2^32-1 / 2^96 = -1
+//      folding stays a hand-written carry chain;
+//  (b) the circulant MDS is evaluated in the "frequency domain" of the length-12 cyclic convolution
+//      (x^12 - 1 = prod_{y^4=1} (x^3 - y): 4-point DFTs of the three stride-3 subsequences, a 3x3 block product per
+//      frequency, inverse DFTs).  The Poseidon MDS was chosen so that the block constants are tiny: {16,16,32},
+//      {-1,-2,8}, {2+i, 1+16i, 1-4i} (derived and checked against the direct sum by tools/gen_mds_freq.py).  All values
+//      are integers below 2^53, so the FP64 pipe computes them exactly: 88 DADD/DFMA per 32-bit half instead of 144;
+//  (c) partial rounds run in pairs: between the two MDS layers of a pair only element 0 (the one that passes the S-box)
+//      is brought back to a 64-bit residue; elements 1..11 stay as exact double halves (< 2^40.1 after one layer,
+//      < 2^48.2 after two, intermediates < 300 * 2^40.1 < 2^49), saving 11 of 12 recombine+split steps every other round.
+__device__ __forceinline__ u64 p9_mul(u64 a, u64 b) {
+    unsigned __int128 pr = (unsigned __int128)a * b;
+    u64 lo = (u64)pr, hi = (u64)(pr >> 64);
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32);
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 s0,s1,t0,tt1,b,c,m;\n\t"
+        "add.cc.u32 s0, %4, %5;\n\taddc.u32 s1, 0, 0;\n\t"
+        "sub.cc.u32 t0, %2, s0;\n\tsubc.cc.u32 tt1, %3, s1;\n\tsubc.u32 b, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
+        "add.cc.u32 tt1, tt1, %4;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return (u64)o0 | ((u64)o1 << 32);
+}
+__device__ __forceinline__ u64 p9_sbox7(u64 x) {
+    u64 x2 = p9_mul(x, x);
+    u64 x3 = p9_mul(x2, x);
+    u64 x4 = p9_mul(x2, x2);
+    return p9_mul(x3, x4);
+}
+// exact integer MDS on 12 doubles (one 32-bit half of every state word, or an unreduced half from the previous layer)
+__device__ __forceinline__ void p9_mds_half(const double* x, double* o) {
+    double S1[3], Sm[3], Sr[3], Si[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        double e0 = x[b] + x[6 + b], e1 = x[3 + b] + x[9 + b];
+        Sr[b] = x[b] - x[6 + b]; Si[b] = x[3 + b] - x[9 + b];
+        S1[b] = e0 + e1; Sm[b] = e0 - e1;
+    }
+    // y = 1 : rows of {16,16,32}
+    const double t16 = ((S1[0] + S1[1]) + S1[2]) * 16.0;
+    const double A0 = fma(S1[2], 16.0, t16), A1 = fma(S1[0], 16.0, t16), A2 = fma(S1[1], 16.0, t16);
+    // y = -1 : {-1,-2,8}, {-8,-1,-2}, {2,-8,-1}
+    const double B0 = fma(Sm[2], 8.0, fma(Sm[1], -2.0, -Sm[0]));
+    const double B1 = fma(Sm[0], -8.0, fma(Sm[2], -2.0, -Sm[1]));
+    const double B2 = fma(Sm[1], -8.0, fma(Sm[0], 2.0, -Sm[2]));
+    // y = i : {2+i, 1+16i, 1-4i}, {-4-i, 2+i, 1+16i}, {16-i, -4-i, 2+i};  P = sum Sr*gr - Si*gi, Q = sum Sr*gi + Si*gr
+    const double P0 = fma(Si[2], 4.0, fma(Si[1], -16.0, fma(Sr[0], 2.0, (Sr[1] + Sr[2]) - Si[0])));
+    const double Q0 = fma(Sr[2], -4.0, fma(Sr[1], 16.0, fma(Si[0], 2.0, (Si[1] + Si[2]) + Sr[0])));
+    const double P1 = fma(Si[2], -16.0, fma(Sr[1], 2.0, fma(Sr[0], -4.0, (Sr[2] + Si[0]) - Si[1])));
+    const double Q1 = fma(Sr[2], 16.0, fma(Si[1], 2.0, fma(Si[0], -4.0, (Si[2] - Sr[0]) + Sr[1])));
+    const double P2 = fma(Sr[2], 2.0, fma(Sr[1], -4.0, fma(Sr[0], 16.0, (Si[0] + Si[1]) - Si[2])));
+    const double Q2 = fma(Si[2], 2.0, fma(Si[1], -4.0, fma(Si[0], 16.0, Sr[2] - (Sr[0] + Sr[1]))));
+    const double u0 = A0 + B0, v0 = A0 - B0, u1 = A1 + B1, v1 = A1 - B1, u2 = A2 + B2, v2 = A2 - B2;
+    o[0] = fma(x[0], 8.0, u0 + P0); o[3] = v0 + Q0; o[6] = u0 - P0; o[9] = v0 - Q0;
+    o[1] = u1 + P1; o[4] = v1 + Q1; o[7] = u1 - P1; o[10] = v1 - Q1;
+    o[2] = u2 + P2; o[5] = v2 + Q2; o[8] = u2 - P2; o[11] = v2 - Q2;
+}
+// al + ah * 2^32 (exact non-negative integers < 2^52 held in doubles) -> lazy residue
+__device__ __forceinline__ u64 p9_recombine(double al, double ah) {
+    double tl = al + 4503599627370496.0, th = ah + 4503599627370496.0;
+    u32 al0 = (u32)__double2loint(tl), al1 = (u32)__double2hiint(tl) & 0xfffffu;
+    u32 ah0 = (u32)__double2loint(th), ah1 = (u32)__double2hiint(th) & 0xfffffu;
+    u32 o0, o1;
+    asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
+        "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"
+        "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"
+        "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
+        "sub.u32 m, 0, cy;\n\t"
+        "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
+    return (u64)o0 | ((u64)o1 << 32);
+}
+__device__ __forceinline__ void p9_sbox_layer(u64* s) {
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        u64 a = p9_sbox7(s[0]), b = p9_sbox7(s[1]), c = p9_sbox7(s[2]), d = p9_sbox7(s[3]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+        s[8] = a; s[9] = b; s[10] = c; s[11] = d;
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void poseidon_permute_v9_t(u64* s) {
+    // 19 steps: 4 full rounds, 11 pairs of partial rounds, 4 full rounds (merged partial-round constants as in v8)
+#pragma unroll 1
+    for (int st = 0; st < 19; st++) {
+        const bool full = (st < 4) || (st >= 15);
+        double lo[12], hi[12];
+        if (full) {
+            const int r = st < 4 ? st : st + 11;
+            const u64* rc = (r == 26) ? D_POSEIDON_RC26_MERGED : (D_POSEIDON_RC + 12 * r);
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], rc[i]);
+            p9_sbox_layer(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+        } else {
+            const int r = 4 + 2 * (st - 4);
+            s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 4]));
+            double xl[12], xh[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) { xl[i] = p3_u32_to_f64((u32)s[i]); xh[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+            p9_mds_half(xl, lo);
+            p9_mds_half(xh, hi);
+            if (PAIR) {
+                u64 s0 = p9_sbox7(p2_add_canon(p9_recombine(lo[0], hi[0]), D_POSEIDON_PARTIAL_A[r - 3]));
+                lo[0] = p3_u32_to_f64((u32)s0); hi[0] = p3_u32_to_f64((u32)(s0 >> 32));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) s[i] = p9_recombine(lo[i], hi[i]);
+                s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 3]));
+#pragma unroll
+                for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+            }
+        }
+        double al[12], ah[12];
+        p9_mds_half(lo, al);
+        p9_mds_half(hi, ah);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p9_recombine(al[i], ah[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
+__device__ __forceinline__ void poseidon_permute_v9(u64* s) { poseidon_permute_v9_t<true>(s); }
+// the permutation every product kernel calls (ZKM_POSEIDON_V8 selects the previous generation for A/B timing)
+#ifdef ZKM_POSEIDON_V8
+#define poseidon_permute_dev poseidon_permute_v8
+#else
+#define poseidon_permute_dev poseidon_permute_v9
+#endif
+
 __device__ __forceinline__ void poseidon_permute_v6(u64* s) {
     int rc = 0;
 #pragma unroll 1

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(128, MINB) k_perm_vx(const u64* __restrict__ i
         else if (V == 6) poseidon_permute_v6(s);
         else if (V == 8) poseidon_permute_v8(s);
         else if (V == 9) poseidon_permute_v9_t<true>(s);
+        else if (V >= 20 && V < 28) poseidon_permute_v9_t<true, V - 20>(s);
         else poseidon_permute_v9_t<false>(s);
     }
 #pragma unroll
@@ -157,6 +158,12 @@ int main() {
     timeit("v9 freq-mds paired lb(128,5)", [&] { k_perm_vx<9, 5><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v9 freq-mds paired lb(128,4)", [&] { k_perm_vx<9, 4><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v9 freq-mds paired lb(128,8)", [&] { k_perm_vx<9, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps);
+    timeit("v9 cv1 (I2F split) lb(128,8)", [&] { k_perm_vx<21, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9cv1");
+    timeit("v9 cv2 (F2I recombine) lb(128,8)", [&] { k_perm_vx<22, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9cv2");
+    timeit("v9 cv3 (I2F+F2I) lb(128,8)", [&] { k_perm_vx<23, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9cv3");
+    timeit("v9 cv4 (mad.wide pack) lb(128,8)", [&] { k_perm_vx<24, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9cv4");
+    timeit("v9 cv6 (mad.wide+F2I) lb(128,8)", [&] { k_perm_vx<26, 8><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v9cv6");
+    timeit("v9 cv3 (I2F+F2I) lb(128,6)", [&] { k_perm_vx<23, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v10 freq-mds unpaired lb(128,6)", [&] { k_perm_vx<10, 6><<<g, 128>>>(din, dout, count, reps); }, count, reps); check("v10");
     timeit("v10 freq-mds unpaired lb(128,5)", [&] { k_perm_vx<10, 5><<<g, 128>>>(din, dout, count, reps); }, count, reps);
     timeit("v2 x2 states/thread", [&] { k_perm_x2<<<g / 2, 128>>>(din, dout, count, reps); }, count, reps);

@@ -18,7 +18,7 @@ __device__ __forceinline__ size_t lde_pos_of_leaf(u32 leaf, int log_n, int rate_
     return ((size_t)j << log_n) + i;
 }
 
-__global__ void __launch_bounds__(128, 6) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
+__global__ void __launch_bounds__(128, 8) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
                                                             int rate_bits, u64* __restrict__ dig) {
     const size_t N = (size_t)1 << (log_n + rate_bits);
     size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, 6) lde_leaf_hash_kernel(const u64* __rest
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-__global__ void __launch_bounds__(128, 6) rows_leaf_hash_kernel(const u64* __restrict__ rows, int width, size_t num_leaves,
+__global__ void __launch_bounds__(128, 8) rows_leaf_hash_kernel(const u64* __restrict__ rows, int width, size_t num_leaves,
                                                              u64* __restrict__ dig) {
     size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= num_leaves) return;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128, 6) rows_leaf_hash_kernel(const u64* __res
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-__global__ void __launch_bounds__(128, 6) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+__global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parents) return;
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);

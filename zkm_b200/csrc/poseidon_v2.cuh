@@ -263,11 +263,32 @@ __device__ __forceinline__ void p9_mds_half(const double* x, double* o) {
     o[1] = u1 + P1; o[4] = v1 + Q1; o[7] = u1 - P1; o[10] = v1 - Q1;
     o[2] = u2 + P2; o[5] = v2 + Q2; o[8] = u2 - P2; o[11] = v2 - Q2;
 }
-// al + ah * 2^32 (exact non-negative integers < 2^52 held in doubles) -> lazy residue
+// u32 -> double.  CV bit 0: I2F.F64.U32 on the XU pipe (one instruction, otherwise idle pipe) instead of the 2^52
+// magic-number packing (a DADD plus register moves on the FP64/FMA pipes, the busiest ones after the v9 changes);
+// CV bit 2: pack the magic-number double with one IMAD.WIDE (x * 1 + 0x4330000000000000) instead of two moves.
+template <int CV>
+__device__ __forceinline__ double p9_cvt(u32 x) {
+    if (CV & 1) return (double)x;
+    if (CV & 4) {
+        u64 t;
+        asm("mad.wide.u32 %0, %1, 1, 0x4330000000000000;" : "=l"(t) : "r"(x));
+        return __longlong_as_double((long long)t) - 4503599627370496.0;
+    }
+    return p3_u32_to_f64(x);
+}
+// al + ah * 2^32 (exact non-negative integers < 2^52 held in doubles) -> lazy residue.  CV bit 1: F2I.U64.F64 (XU pipe)
+// instead of DADD + mask.
+template <int CV>
 __device__ __forceinline__ u64 p9_recombine(double al, double ah) {
-    double tl = al + 4503599627370496.0, th = ah + 4503599627370496.0;
-    u32 al0 = (u32)__double2loint(tl), al1 = (u32)__double2hiint(tl) & 0xfffffu;
-    u32 ah0 = (u32)__double2loint(th), ah1 = (u32)__double2hiint(th) & 0xfffffu;
+    u32 al0, al1, ah0, ah1;
+    if (CV & 2) {
+        u64 a = __double2ull_rz(al), b = __double2ull_rz(ah);
+        al0 = (u32)a; al1 = (u32)(a >> 32); ah0 = (u32)b; ah1 = (u32)(b >> 32);
+    } else {
+        double tl = al + 4503599627370496.0, th = ah + 4503599627370496.0;
+        al0 = (u32)__double2loint(tl); al1 = (u32)__double2hiint(tl) & 0xfffffu;
+        ah0 = (u32)__double2loint(th); ah1 = (u32)__double2hiint(th) & 0xfffffu;
+    }
     u32 o0, o1;
     asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
         "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"
@@ -287,7 +308,7 @@ __device__ __forceinline__ void p9_sbox_layer(u64* s) {
         s[8] = a; s[9] = b; s[10] = c; s[11] = d;
     }
 }
-template <bool PAIR>
+template <bool PAIR, int CV = 0>
 __device__ __forceinline__ void poseidon_permute_v9_t(u64* s) {
     // 19 steps: 4 full rounds, 11 pairs of partial rounds, 4 full rounds (merged partial-round constants as in v8)
 #pragma unroll 1
@@ -301,31 +322,31 @@ __device__ __forceinline__ void poseidon_permute_v9_t(u64* s) {
             for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], rc[i]);
             p9_sbox_layer(s);
 #pragma unroll
-            for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+            for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
         } else {
             const int r = 4 + 2 * (st - 4);
             s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 4]));
             double xl[12], xh[12];
 #pragma unroll
-            for (int i = 0; i < 12; i++) { xl[i] = p3_u32_to_f64((u32)s[i]); xh[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+            for (int i = 0; i < 12; i++) { xl[i] = p9_cvt<CV>((u32)s[i]); xh[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
             p9_mds_half(xl, lo);
             p9_mds_half(xh, hi);
             if (PAIR) {
-                u64 s0 = p9_sbox7(p2_add_canon(p9_recombine(lo[0], hi[0]), D_POSEIDON_PARTIAL_A[r - 3]));
-                lo[0] = p3_u32_to_f64((u32)s0); hi[0] = p3_u32_to_f64((u32)(s0 >> 32));
+                u64 s0 = p9_sbox7(p2_add_canon(p9_recombine<CV>(lo[0], hi[0]), D_POSEIDON_PARTIAL_A[r - 3]));
+                lo[0] = p9_cvt<CV>((u32)s0); hi[0] = p9_cvt<CV>((u32)(s0 >> 32));
             } else {
 #pragma unroll
-                for (int i = 0; i < 12; i++) s[i] = p9_recombine(lo[i], hi[i]);
+                for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(lo[i], hi[i]);
                 s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 3]));
 #pragma unroll
-                for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
+                for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
             }
         }
         double al[12], ah[12];
         p9_mds_half(lo, al);
         p9_mds_half(hi, ah);
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p9_recombine(al[i], ah[i]);
+        for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(al[i], ah[i]);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cols", type=int, default=54)
 ap.add_argument("--logn", type=int, default=20)
 ap.add_argument("--prove", type=int, default=0)
+ap.add_argument("--warm", type=int, default=0)
+ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 lib = zl.init(0)
 err = C.c_void_p()
@@ -30,7 +32,12 @@ if a.cols:
     zl.check(lib, lib.zkm_b200_commit_values_device(buf.data_ptr(), a.cols, a.logn, 2, 4, C.byref(h), zl.u64ptr(cap), C.byref(err)), err)
     lib.zkm_b200_batch_free(h)
 if a.prove:
+    import os
     seg = bench.Segment(lib, f"U{a.prove}")
+    for _ in range(a.warm):
+        seg.step_device()
+    if a.trace:
+        os.environ["ZKM_TRACE"] = "1"      # host wall-clock per prover phase (steady state after the warm proofs)
     seg.step_device()
     seg.sync()
 print("prof_target done")

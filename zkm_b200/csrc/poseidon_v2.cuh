@@ -351,7 +351,7 @@ __device__ __forceinline__ void poseidon_permute_v9_t(u64* s) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
 }
-__device__ __forceinline__ void poseidon_permute_v9(u64* s) { poseidon_permute_v9_t<true>(s); }
+__device__ __forceinline__ void poseidon_permute_v9(u64* s) { poseidon_permute_v9_t<true, 3>(s); }
 // the permutation every product kernel calls (ZKM_POSEIDON_V8 selects the previous generation for A/B timing)
 #ifdef ZKM_POSEIDON_V8
 #define poseidon_permute_dev poseidon_permute_v8

@@ -152,6 +152,10 @@ int zkm_b200_batch_open(const zkm_batch_t* b, uint32_t leaf_index, uint64_t* lea
 int zkm_b200_ntt(uint64_t* data, uint32_t ncols, uint32_t log_n, int kind, char** err);
 /* Poseidon permutations on `count` independent 12-word states (host buffer), run on the GPU. */
 int zkm_b200_poseidon_permute(uint64_t* states, size_t count, char** err);
+/* The permutation of the prover's host-side Fiat-Shamir transcript (plonky2 iop/challenger.rs duplexing as reached from
+ * reference prover/src/prover.rs:182-190,466,524-527,588-591,610), on `count` independent 12-word states in place.
+ * Runs on the CPU, needs no device and no zkm_b200_init: exported so the transcript's hash can be checked on its own. */
+int zkm_b200_transcript_permute(uint64_t* states, size_t count, char** err);
 
 #ifdef __cplusplus
 }

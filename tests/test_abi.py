@@ -47,3 +47,29 @@ def test_no_cpu_fallback_without_gpu():
     msg = C.cast(err, C.c_char_p).value.decode()
     assert "no CPU fallback" in msg or "CUDA" in msg
     lib.zkm_b200_free_string(err)
+
+
+def test_transcript_permutation_matches_oracle(orc):
+    """The host-side Fiat-Shamir permutation of the prover (fast CPU schedule, csrc/poseidon_host.h) against the oracle's
+    naive schedule and the known answers of SURVEY Appendix D.  Needs no GPU."""
+    import numpy as np
+    from oracle import binding
+    from zkm_b200.lib import load, u64ptr
+    from conftest import splitmix64_stream, P
+    lib = load()
+    n = 4096
+    st = splitmix64_stream(0xC0FFEE, 12 * n).reshape(n, 12).copy()
+    st[0] = 0
+    st[1] = np.arange(12, dtype=np.uint64)
+    st[2] = np.uint64(P - 1)
+    st[3, ::2] = np.uint64(P - 1)
+    want = st.copy()
+    for i in range(n):
+        row = np.ascontiguousarray(want[i])
+        orc.orc_poseidon_permute(binding.u64ptr(row), 0)
+        want[i] = row
+    got = np.ascontiguousarray(st)
+    err = C.c_void_p()
+    assert lib.zkm_b200_transcript_permute(u64ptr(got), n, C.byref(err)) == 0
+    assert (got == want).all()
+    assert int(got[0, 0]) == 0x3c18a9786cb0b359 and int(got[1, 0]) == 0xd64e1e3efc5b8e9e

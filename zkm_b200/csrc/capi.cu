@@ -3,6 +3,7 @@
 #include "../../include/zkm_b200.h"
 #include "batch.cuh"
 #include "poseidon_v2.cuh"
+#include "poseidon_host.h"
 #include "prover.cuh"
 #include "tables/systems.h"
 #include <cstring>
@@ -443,6 +444,12 @@ int zkm_b200_poseidon_permute(uint64_t* states, size_t count, char** err) {
         ZKM_LAUNCHED();
         d.download(states, count * 12);
     }
+    ZKM_API_END
+}
+
+int zkm_b200_transcript_permute(uint64_t* states, size_t count, char** err) {
+    ZKM_API_BEGIN
+    for (size_t i = 0; i < count; i++) poseidon_permute_host(states + 12 * i);
     ZKM_API_END
 }
 

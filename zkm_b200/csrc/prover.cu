@@ -6,6 +6,7 @@
 #include "prover.cuh"
 #include "fri.cuh"
 #include "poseidon.cuh"
+#include "poseidon_host.h"
 #include "tables/systems.h"
 #include <cstring>
 #include <chrono>
@@ -39,7 +40,7 @@ struct HostChallenger {
     void duplexing() {
         for (size_t i = 0; i < in.size(); i++) state[i] = in[i];
         in.clear();
-        poseidon_permute(state);
+        poseidon_permute_host(state);      // fast CPU schedule (poseidon_host.h): the transcript is serial host work
         out.assign(state, state + 8);
     }
     void observe(u64 x) {

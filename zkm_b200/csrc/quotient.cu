@@ -36,10 +36,18 @@ __device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
     return r;
 }
 
+// Small tables (2n points fill a few CTAs at most) are latency bound: one thread walks the whole interpreted CTL/lookup
+// program, two dependent loads per term, with one warp per scheduler and nothing to hide the latency (KeccakSponge at
+// 2^6 rows: 8.7 ms for 128 points).  The cooperative variant gives every point W worker threads (threadIdx.y): the
+// helper-column constraint VALUES, which are independent of each other, are computed by the workers in parallel into
+// shared memory, and every worker then folds them in emission order, so the result is bit-identical.
+constexpr int COOP_CHUNK = 16;          // helper constraints per shared-memory round
 struct DevConsumer {
     gl alpha[QUOTIENT_ALPHAS], acc[QUOTIENT_ALPHAS];
     int na;
     gl z_last, l_first, l_last;
+    int worker = 0, workers = 1, px = 0, npx = 0;      // cooperative mode: this thread's worker id, point slot
+    u64* stage = nullptr;                              // shared memory [COOP_CHUNK][npx]
     __device__ __forceinline__ void constraint(gl c) {
         FoldPair r = quotient_fold(acc[0].v, acc[1].v, c.v);
         acc[0] = gl(r.a0); acc[1] = gl(r.a1);
@@ -74,32 +82,47 @@ __device__ __forceinline__ gl dcol_eval_local(const DProgramView& P, int ci, con
 }
 
 // eval_helper_columns (cross_table_lookup.rs:1006-1057) for parts [part_off, part_off + part_cnt).
+__device__ __forceinline__ gl dev_helper_value(const DProgramView& P, int part_off, int part_cnt, int j, const LdeRow& lv, const LdeRow& nv,
+                                               const LdeRow& al, int helper_aux, gl beta, gl gamma) {
+    gl h = al[helper_aux + j];
+    const DPart p0 = P.parts[part_off + 2 * j];
+    gl c0 = dpart_combine(P, p0, lv, nv, beta, gamma);
+    gl f0 = dfilter_eval(P, p0.filter, lv, nv);
+    if (2 * j + 1 < part_cnt) {
+        const DPart p1 = P.parts[part_off + 2 * j + 1];
+        gl c1 = dpart_combine(P, p1, lv, nv, beta, gamma);
+        gl f1 = dfilter_eval(P, p1.filter, lv, nv);
+        return c1 * c0 * h - f0 * c1 - f1 * c0;
+    }
+    return c0 * h - f0;
+}
+template <bool COOP>
 __device__ __forceinline__ void dev_eval_helper_columns(const DProgramView& P, int part_off, int part_cnt, int num_helpers, const LdeRow& lv,
                                                         const LdeRow& nv, const LdeRow& al, int helper_aux, gl beta, gl gamma, DevConsumer& yc) {
     if (num_helpers == 0) return;
-    for (int j = 0; 2 * j < part_cnt; j++) {
-        gl h = al[helper_aux + j];
-        const DPart p0 = P.parts[part_off + 2 * j];
-        gl c0 = dpart_combine(P, p0, lv, nv, beta, gamma);
-        gl f0 = dfilter_eval(P, p0.filter, lv, nv);
-        if (2 * j + 1 < part_cnt) {
-            const DPart p1 = P.parts[part_off + 2 * j + 1];
-            gl c1 = dpart_combine(P, p1, lv, nv, beta, gamma);
-            gl f1 = dfilter_eval(P, p1.filter, lv, nv);
-            yc.constraint(c1 * c0 * h - f0 * c1 - f1 * c0);
-        } else {
-            yc.constraint(c0 * h - f0);
-        }
+    const int nh = (part_cnt + 1) / 2;
+    if (!COOP) {
+        for (int j = 0; j < nh; j++) yc.constraint(dev_helper_value(P, part_off, part_cnt, j, lv, nv, al, helper_aux, beta, gamma));
+        return;
+    }
+    for (int j0 = 0; j0 < nh; j0 += COOP_CHUNK) {
+        const int cnt = nh - j0 < COOP_CHUNK ? nh - j0 : COOP_CHUNK;
+        for (int jj = yc.worker; jj < cnt; jj += yc.workers)
+            yc.stage[jj * yc.npx + yc.px] = dev_helper_value(P, part_off, part_cnt, j0 + jj, lv, nv, al, helper_aux, beta, gamma).v;
+        __syncthreads();
+        for (int jj = 0; jj < cnt; jj++) yc.constraint(gl(yc.stage[jj * yc.npx + yc.px]));
+        __syncthreads();
     }
 }
 
+template <bool COOP>
 __device__ __forceinline__ void dev_eval_lookups(const QParams& q, const LdeRow& lv, const LdeRow& nv, const LdeRow& al, const LdeRow& an,
                                                  DevConsumer& yc) {
     const DProgramView& P = q.prog;
     for (int li = 0; li < P.num_lookups; li++) {
         const DLookup l = P.lookups[li];
         gl challenge(q.ch.beta[l.challenge]);
-        dev_eval_helper_columns(P, l.part_off, l.part_cnt, l.num_helpers, lv, nv, al, l.aux_start, gl::one(), challenge, yc);
+        dev_eval_helper_columns<COOP>(P, l.part_off, l.part_cnt, l.num_helpers, lv, nv, al, l.aux_start, gl::one(), challenge, yc);
         gl z = al[l.aux_start + l.num_helpers], next_z = an[l.aux_start + l.num_helpers];
         gl twc = dcol_eval_local(P, l.table_col, lv) + challenge;
         gl hs = gl::zero();
@@ -110,13 +133,14 @@ __device__ __forceinline__ void dev_eval_lookups(const QParams& q, const LdeRow&
     }
 }
 
+template <bool COOP>
 __device__ __forceinline__ void dev_eval_ctl_checks(const QParams& q, const LdeRow& lv, const LdeRow& nv, const LdeRow& al, const LdeRow& an,
                                                     DevConsumer& yc) {
     const DProgramView& P = q.prog;
     for (int zi = 0; zi < P.num_zs; zi++) {
         const DZ z = P.zs[zi];
         gl beta(q.ch.beta[z.challenge]), gamma(q.ch.gamma[z.challenge]);
-        dev_eval_helper_columns(P, z.part_off, z.part_cnt, z.num_helpers, lv, nv, al, z.helper_aux, beta, gamma, yc);
+        dev_eval_helper_columns<COOP>(P, z.part_off, z.part_cnt, z.num_helpers, lv, nv, al, z.helper_aux, beta, gamma, yc);
         gl local_z = al[z.z_aux], next_z = an[z.z_aux];
         if (z.num_helpers) {
             gl hs = gl::zero();
@@ -152,8 +176,9 @@ __device__ __forceinline__ gl gl_inv_q(gl x) {
     return gl_exp2(x31, 33) * x32;
 }
 
-template <int KIND>
+template <int KIND, bool COOP>
 __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
+    __shared__ u64 coop_stage[COOP ? COOP_CHUNK * 128 : 1];
     const size_t n = (size_t)1 << q.log_n;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the 2n points exactly (no early exit: checkpoints)
     const size_t half = t >> q.log_n, idx = t & (n - 1);
@@ -165,6 +190,7 @@ __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
     gl x = gl(GL_GENERATOR) * pow_lookup(q.w2n, i);
     DevConsumer yc;
     yc.na = q.na;
+    if (COOP) { yc.worker = threadIdx.y; yc.workers = blockDim.y; yc.px = threadIdx.x; yc.npx = blockDim.x; yc.stage = coop_stage; }
 #pragma unroll
     for (int a = 0; a < QUOTIENT_ALPHAS; a++) { yc.alpha[a] = gl(q.alphas[a]); yc.acc[a] = gl::zero(); }
     yc.z_last = x - gl(q.last);
@@ -177,9 +203,10 @@ __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
     yc.l_last = zhx * (inv * d0);
 
     tables::eval_table<gl, LdeRow, DevConsumer>(KIND, lv, nv, yc);
-    if (q.prog.num_lookups) dev_eval_lookups(q, lv, nv, al, an, yc);
-    dev_eval_ctl_checks(q, lv, nv, al, an, yc);
+    if (q.prog.num_lookups) dev_eval_lookups<COOP>(q, lv, nv, al, an, yc);
+    dev_eval_ctl_checks<COOP>(q, lv, nv, al, an, yc);
 
+    if (COOP && threadIdx.y != 0) return;               // every worker holds the same accumulators
     gl zi(q.zh_inv[i & 1]);
 #pragma unroll
     for (int a = 0; a < QUOTIENT_ALPHAS; a++)
@@ -187,9 +214,9 @@ __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
 }
 
 typedef void (*quotient_kernel_t)(QParams);
-static quotient_kernel_t quotient_kernel_for(int kind) {
+static quotient_kernel_t quotient_kernel_for(int kind, bool coop) {
     switch (kind) {
-#define ZKM_QK(k) case tables::k: return quotient_kernel<tables::k>;
+#define ZKM_QK(k) case tables::k: return coop ? quotient_kernel<tables::k, true> : quotient_kernel<tables::k, false>;
         ZKM_QK(T_ARITHMETIC) ZKM_QK(T_CPU) ZKM_QK(T_POSEIDON) ZKM_QK(T_POSEIDON_SPONGE) ZKM_QK(T_KECCAK) ZKM_QK(T_KECCAK_SPONGE)
         ZKM_QK(T_SHA_EXTEND) ZKM_QK(T_SHA_EXTEND_SPONGE) ZKM_QK(T_SHA_COMPRESS) ZKM_QK(T_SHA_COMPRESS_SPONGE) ZKM_QK(T_LOGIC) ZKM_QK(T_MEMORY)
 #undef ZKM_QK
@@ -226,10 +253,17 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
         for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
         ZKM_CUDA(cudaMemcpyToSymbolAsync(c_quotient_alpha, ha, sizeof(ha), 0, cudaMemcpyHostToDevice, s));
     }
-    quotient_kernel_t k = quotient_kernel_for(kind);
+    // cooperative variant while the 2n points cannot fill the machine: 128 points x 4 workers per CTA
+    const bool coop = 2 * n <= 8192;
+    quotient_kernel_t k = quotient_kernel_for(kind, coop);
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
-    const unsigned threads = 2 * n >= 512 ? 512 : (unsigned)(2 * n);
-    k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
+    if (coop) {
+        const unsigned px = 2 * n >= 128 ? 128 : (unsigned)(2 * n);
+        k<<<(unsigned)(2 * n / px), dim3(px, 512 / px), 0, s>>>(q);
+    } else {
+        const unsigned threads = 512;
+        k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
+    }
     ZKM_LAUNCHED();
     ZKM_CUDA(cudaStreamSynchronize(s));                      // keeps `tab` alive until the kernel has run
 }

@@ -30,7 +30,7 @@ EXPORTS = [
     "zkm_b200_free_string", "zkm_b200_free", "zkm_b200_standard_fast_config", "zkm_b200_init", "zkm_b200_shutdown",
     "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
-    "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute",
+    "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
@@ -62,6 +62,7 @@ def load():
     lib.zkm_b200_batch_open.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p, C.POINTER(C.c_void_p)]
     lib.zkm_b200_ntt.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     lib.zkm_b200_poseidon_permute.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_transcript_permute.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkm_b200_synth_columns_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
     u32p = C.POINTER(C.c_uint32)
     lib.zkm_b200_prove_with_traces.argtypes = [C.POINTER(Table), u32p, u32p, C.c_char_p, C.c_uint32, C.POINTER(StarkConfig),

@@ -85,6 +85,53 @@ __global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restr
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
+// Small levels (<= 2^14 parents) cannot fill the machine with one thread per permutation: a level then costs one
+// single-thread permutation latency (~30 us, 11 such levels per 2^22-leaf tree and ~80 trees per proof).  Here 12 lanes
+// share one permutation, one state word each: the S-boxes of a full round run side by side and the MDS row of a lane is
+// 12 shuffled multiply-adds, so the dependent instruction chain is ~4x shorter.  Two permutations per warp (lanes 0-11
+// and 16-27).  Same merged partial-round constants as poseidon_permute_v8; outputs are bit-identical.
+__global__ void __launch_bounds__(128) merkle_level_coop_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+    const unsigned lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
+    const size_t node = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * 2 + grp;
+    const bool live = sub < 12 && node < n_parents;
+    const unsigned base = grp << 4;                      // first lane of this permutation's group
+    u64 s = (live && sub < 8) ? child[node * 8 + sub] : 0;
+    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    const unsigned l = sub < 12 ? sub : 0;
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        if (full) {
+            const u64* rc = (r == 26) ? D_POSEIDON_RC26_MERGED : (D_POSEIDON_RC + 12 * r);
+            s = p9_sbox7(p2_add_canon(s, rc[l]));
+        } else {
+            u64 t = p9_sbox7(p2_add_canon(s, D_POSEIDON_PARTIAL_A[r - 4]));
+            if (l == 0) s = t;
+        }
+        const u32 lo = (u32)s, hi = (u32)(s >> 32);
+        u64 al = 0, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            unsigned src = l + i; src = src >= 12 ? src - 12 : src;
+            al = p2_madw(__shfl_sync(0xffffffffu, lo, base + src), C[i], al);
+            ah = p2_madw(__shfl_sync(0xffffffffu, hi, base + src), C[i], ah);
+        }
+        if (l == 0) { al = p2_madw(lo, 8u, al); ah = p2_madw(hi, 8u, ah); }
+        // value = al + ah * 2^32 (< 2^75), folded as in p2_mds
+        u32 al0 = (u32)al, al1 = (u32)(al >> 32), ah0 = (u32)ah, ah1 = (u32)(ah >> 32);
+        u32 o0, o1;
+        asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
+            "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"
+            "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"
+            "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
+            "sub.u32 m, 0, cy;\n\t"
+            "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
+            : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
+        s = (u64)o0 | ((u64)o1 << 32);
+    }
+    if (live && sub < 4) parent[node * 4 + sub] = lz_canon(s);
+}
+
 void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t s) {
     ZKM_CHECK(cap_height <= log_leaves, "Merkle cap height exceeds tree height");
     t.log_leaves = log_leaves; t.cap_height = cap_height;
@@ -102,8 +149,12 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     ProfScope ps("merkle_levels", s, 48.0 * (double)(t.num_leaves() - ((size_t)1 << t.cap_height)));
     for (int l = 1; l < t.num_levels(); l++) {
         size_t np = (size_t)1 << (t.log_leaves - l);
-        unsigned blocks = (unsigned)((np + 127) / 128);
-        merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+        if (np <= ((size_t)1 << 14)) {
+            merkle_level_coop_kernel<<<(unsigned)((np + 7) / 8), 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+        } else {
+            unsigned blocks = (unsigned)((np + 127) / 128);
+            merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+        }
         ZKM_LAUNCHED();
     }
     }

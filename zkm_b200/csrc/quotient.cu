@@ -27,9 +27,9 @@ constexpr int QUOTIENT_ALPHAS = 2;
 // The alpha-fold acc <- acc * alpha + c runs once per constraint (hundreds of times per point).  It is a
 // NON-inlined function so that its ~55 instructions exist once in the instruction cache instead of once per
 // constraint (the straight-line constraint code is instruction-fetch bound); the alphas live in constant memory.
-__constant__ u64 c_quotient_alpha[QUOTIENT_ALPHAS];
+static __constant__ u64 c_quotient_alpha[QUOTIENT_ALPHAS];     // one copy per translation unit (see the bottom of the file)
 struct FoldPair { u64 a0, a1; };
-__device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
+static __device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
     FoldPair r;
     r.a0 = (gl(a0) * gl(c_quotient_alpha[0]) + gl(c)).v;
     r.a1 = (gl(a1) * gl(c_quotient_alpha[1]) + gl(c)).v;
@@ -41,7 +41,8 @@ __device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
 // 2^6 rows: 8.7 ms for 128 points).  The cooperative variant gives every point W worker threads (threadIdx.y): the
 // helper-column constraint VALUES, which are independent of each other, are computed by the workers in parallel into
 // shared memory, and every worker then folds them in emission order, so the result is bit-identical.
-constexpr int COOP_CHUNK = 16;          // helper constraints per shared-memory round
+constexpr int COOP_CHUNK = 64;          // helper constraints per shared-memory round
+constexpr int COOP_PX = 32;             // points per CTA in cooperative mode (one warp per worker)
 struct DevConsumer {
     gl alpha[QUOTIENT_ALPHAS], acc[QUOTIENT_ALPHAS];
     int na;
@@ -178,7 +179,7 @@ __device__ __forceinline__ gl gl_inv_q(gl x) {
 
 template <int KIND, bool COOP>
 __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
-    __shared__ u64 coop_stage[COOP ? COOP_CHUNK * 128 : 1];
+    __shared__ u64 coop_stage[COOP ? COOP_CHUNK * COOP_PX : 1];
     const size_t n = (size_t)1 << q.log_n;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the 2n points exactly (no early exit: checkpoints)
     const size_t half = t >> q.log_n, idx = t & (n - 1);
@@ -213,16 +214,45 @@ __global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
         if (a < q.na) q.q[(size_t)a * 2 * n + i] = (yc.acc[a] * zi).v;
 }
 
+// The 12 x 2 kernel instantiations are spread over four translation units (quotient.cu = part 0 plus the launcher,
+// quotient_p1..3.cu include this file with ZKM_QPART set) so that they compile in parallel.
 typedef void (*quotient_kernel_t)(QParams);
-static quotient_kernel_t quotient_kernel_for(int kind, bool coop) {
-    switch (kind) {
-#define ZKM_QK(k) case tables::k: return coop ? quotient_kernel<tables::k, true> : quotient_kernel<tables::k, false>;
-        ZKM_QK(T_ARITHMETIC) ZKM_QK(T_CPU) ZKM_QK(T_POSEIDON) ZKM_QK(T_POSEIDON_SPONGE) ZKM_QK(T_KECCAK) ZKM_QK(T_KECCAK_SPONGE)
-        ZKM_QK(T_SHA_EXTEND) ZKM_QK(T_SHA_EXTEND_SPONGE) ZKM_QK(T_SHA_COMPRESS) ZKM_QK(T_SHA_COMPRESS_SPONGE) ZKM_QK(T_LOGIC) ZKM_QK(T_MEMORY)
-#undef ZKM_QK
-        default:
-            throw std::runtime_error(std::string("constraints of table ") + tables::table_name(kind) + " are not available on the device");
+#ifndef ZKM_QPART
+#define ZKM_QPART 0
+#endif
+#define ZKM_QK(k) case tables::k: kern = coop ? quotient_kernel<tables::k, true> : quotient_kernel<tables::k, false>; break;
+// Returns the kernel for `kind` if this translation unit holds it (after loading the alphas into this unit's own
+// constant-memory copy), else nullptr.
+#define ZKM_QPART_FN(name, cases)                                                                          \
+    quotient_kernel_t name(int kind, bool coop, const u64* host_alphas, cudaStream_t s) {                  \
+        quotient_kernel_t kern = nullptr;                                                                  \
+        switch (kind) { cases default: break; }                                                            \
+        if (kern) ZKM_CUDA(cudaMemcpyToSymbolAsync(c_quotient_alpha, host_alphas, sizeof(u64) * QUOTIENT_ALPHAS, 0, \
+                                                   cudaMemcpyHostToDevice, s));                           \
+        return kern;                                                                                       \
     }
+#if ZKM_QPART == 0
+ZKM_QPART_FN(quotient_kernels_part0, ZKM_QK(T_CPU))
+#elif ZKM_QPART == 1
+ZKM_QPART_FN(quotient_kernels_part1, ZKM_QK(T_ARITHMETIC) ZKM_QK(T_KECCAK) ZKM_QK(T_LOGIC))
+#elif ZKM_QPART == 2
+ZKM_QPART_FN(quotient_kernels_part2, ZKM_QK(T_POSEIDON) ZKM_QK(T_POSEIDON_SPONGE) ZKM_QK(T_KECCAK_SPONGE) ZKM_QK(T_MEMORY))
+#else
+ZKM_QPART_FN(quotient_kernels_part3, ZKM_QK(T_SHA_EXTEND) ZKM_QK(T_SHA_EXTEND_SPONGE) ZKM_QK(T_SHA_COMPRESS) ZKM_QK(T_SHA_COMPRESS_SPONGE))
+#endif
+#undef ZKM_QK
+
+#if ZKM_QPART == 0
+quotient_kernel_t quotient_kernels_part1(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
+quotient_kernel_t quotient_kernels_part2(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
+quotient_kernel_t quotient_kernels_part3(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
+static quotient_kernel_t quotient_kernel_for(int kind, bool coop, const u64* host_alphas, cudaStream_t s) {
+    quotient_kernel_t k = quotient_kernels_part0(kind, coop, host_alphas, s);
+    if (!k) k = quotient_kernels_part1(kind, coop, host_alphas, s);
+    if (!k) k = quotient_kernels_part2(kind, coop, host_alphas, s);
+    if (!k) k = quotient_kernels_part3(kind, coop, host_alphas, s);
+    if (!k) throw std::runtime_error(std::string("constraints of table ") + tables::table_name(kind) + " are not available on the device");
+    return k;
 }
 
 void compute_quotient_values(int kind, const DProgram& prog, const tables::TableLayout& L, const Batch& trace, const Batch& aux,
@@ -248,18 +278,15 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     gl g = gl_root_of_unity(log_n);
     q.g = g.v; q.last = gl_inv(g).v; q.n_inv = gl_inv(gl((u64)n)).v;
     q.q = d_q;
-    {
-        u64 ha[QUOTIENT_ALPHAS] = {0, 0};
-        for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
-        ZKM_CUDA(cudaMemcpyToSymbolAsync(c_quotient_alpha, ha, sizeof(ha), 0, cudaMemcpyHostToDevice, s));
-    }
-    // cooperative variant while the 2n points cannot fill the machine: 128 points x 4 workers per CTA
+    u64 ha[QUOTIENT_ALPHAS] = {0, 0};
+    for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
+    // cooperative variant while the 2n points cannot fill the machine: 32 points x 16 workers per CTA
     const bool coop = 2 * n <= 8192;
-    quotient_kernel_t k = quotient_kernel_for(kind, coop);
+    quotient_kernel_t k = quotient_kernel_for(kind, coop, ha, s);
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
     if (coop) {
-        const unsigned px = 2 * n >= 128 ? 128 : (unsigned)(2 * n);
-        k<<<(unsigned)(2 * n / px), dim3(px, 512 / px), 0, s>>>(q);
+        const unsigned px = 2 * n >= (size_t)COOP_PX ? COOP_PX : (unsigned)(2 * n);
+        k<<<(unsigned)(2 * n / px), dim3(px, 16), 0, s>>>(q);
     } else {
         const unsigned threads = 512;
         k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
@@ -267,5 +294,7 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     ZKM_LAUNCHED();
     ZKM_CUDA(cudaStreamSynchronize(s));                      // keeps `tab` alive until the kernel has run
 }
+
+#endif  // ZKM_QPART == 0
 
 }  // namespace zkm

@@ -429,6 +429,16 @@ def main():
                                         "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0),
                                         "share": v["ms"] / total_ms} for k, v in fam.items()},
                 "dominant_family": top[0],
+                # the same figures for the family that dominates the step (Poseidon leaf hashing: FP64/ALU issue bound, its
+                # HBM fraction is tiny by construction: 8 B per column per leaf against ~18 500 instructions per permutation)
+                "roofline_dominant": {"bound": "hbm", "kernel": top[0],
+                                      "achieved": top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9 if top[1]["ms"] else 0.0,
+                                      "peak": peak, "unit": "GB/s",
+                                      "frac": (top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9 / peak) if top[1]["ms"] else 0.0,
+                                      "traffic": seg.ncu_traffic(top[0]), "launches": top[1]["launches"],
+                                      "avg_launch_ms": top[1]["ms"] / max(1, top[1]["launches"]),
+                                      "share_of_step": top[1]["ms"] / total_ms,
+                                      "note": "issue-bound integer/FP64 kernel; see DESIGN.md section 3 for the pipe-level bound"},
                 "clocks": clk.summary()}
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_pass(args.workload, os.cpu_count() or 1, sample_only=False)

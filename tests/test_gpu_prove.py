@@ -96,3 +96,14 @@ def test_all_stark_synthetic_proof_equals_oracle(zkm, orc):
     gpu = zl.prove_system(zkm, tr.SYSTEM_ALL_STARK, traces)
     cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
     assert _first_diff(gpu, cpu) is None
+
+
+def test_all_stark_synthetic_proof_equals_oracle_mid_heights(zkm, orc):
+    """Same as above with the Cpu, Logic and Memory tables at 2^13 rows and Arithmetic at 2^16: these sizes take the
+    one-thread-per-point quotient kernels, the two-pass NTT and three FRI rounds (the 2^6-row tables take the
+    cooperative small-table kernels), i.e. the code paths the 2^20-row benchmark runs."""
+    heights = [16, 13, 6, 6, 6, 6, 6, 6, 6, 6, 13, 13]
+    traces = zl.synth_traces(zkm, tr.SYSTEM_ALL_STARK, heights)
+    gpu = zl.prove_system(zkm, tr.SYSTEM_ALL_STARK, traces)
+    cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
+    assert _first_diff(gpu, cpu) is None

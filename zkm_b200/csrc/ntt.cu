@@ -17,6 +17,7 @@
 #include "dev.cuh"
 #include "poseidon_v2.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace zkm {
 
@@ -207,6 +208,8 @@ static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s) {
     // one radix-16 work item per thread per step when the tile is large enough (8 warps per SM sub-partition)
     size_t items = (R >> (log_r >= 4 ? 4 : log_r)) * (size_t)p.T;
     int threads = items >= 1024 ? 1024 : (items >= 512 ? 512 : 256);
+    static const int tune_threads = std::getenv("ZKM_NTT_THREADS") ? atoi(std::getenv("ZKM_NTT_THREADS")) : 0;   // tuning sweeps only
+    if (tune_threads && (size_t)tune_threads <= items) threads = tune_threads;
     k<<<grid, threads, smem, s>>>(p);
     ZKM_LAUNCHED();
 }
@@ -272,8 +275,10 @@ static void plan(int log_n, int& l1, int& l2, int& T) {
     l2 = log_n / 2; l1 = log_n - l2;
     int lmax = l1;   // l1 >= l2
     T = (1 << 13) >> lmax;      // <= 8192 elements (66 KB + pad) per tile: 3 CTAs per SM overlap their load/compute/store phases
-    if (T > 8) T = 8;
+    if (T > 4) T = 4;           // sweep on B200 (tools/ntt_sweep.sh, 54 x 2^20): T = 4: 8.65 ms, 8: 8.90, 2: 9.18, 16: 10.2
     if (T < 2) T = 2;
+    static const int tune_T = std::getenv("ZKM_NTT_T") ? atoi(std::getenv("ZKM_NTT_T")) : 0;                     // tuning sweeps only
+    if (tune_T) T = tune_T;
 }
 
 // One size-n transform per (column, z).  shifts: optional pre-scale tables per z (coset).

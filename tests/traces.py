@@ -5,8 +5,8 @@ poseidon/poseidon_stark.rs:105-145 (via the oracle's orc_gen_poseidon_rows)."""
 import numpy as np
 
 P = 0xFFFFFFFF00000001
-SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY = 0, 1, 2, 3, 4
-T_POSEIDON, T_LOGIC, T_MEMORY = 2, 10, 11
+SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH = 0, 1, 2, 3, 4, 5
+T_ARITHMETIC, T_POSEIDON, T_LOGIC, T_MEMORY = 0, 2, 10, 11
 
 
 def logic_trace(log_n: int, seed: int = 1, used_frac: float = 0.8) -> np.ndarray:
@@ -94,3 +94,9 @@ def poseidon_trace(orc, log_n: int, seed: int = 3, used_frac: float = 0.75) -> n
     orc.orc_gen_poseidon_rows(u64ptr(inputs), u64ptr(tsv), n, u64ptr(rows))
     rows[used:, 0] = 0
     return np.ascontiguousarray(rows.T)
+
+
+def arithmetic_trace(count: int = 30000, seed: int = 11, log_n: int = 16) -> np.ndarray:
+    """(54, 2^16) uint64: `count` random operations of all 26 kinds (tests/arith_gen.py)."""
+    import arith_gen as ag
+    return ag.arithmetic_trace(ag.random_ops(count, seed), log_n)

@@ -8,7 +8,7 @@
 namespace zkm {
 namespace tables {
 
-enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4 };
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5 };
 
 // A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
 inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
@@ -36,6 +36,14 @@ inline System make_system(int id) {
             s.kinds = {T_MEMORY};
             s.ctls.push_back(self_ctl(0, memory::ctl_data(), memory::ctl_filter()));
             return s;
+        case SYSTEM_ARITH: {
+            // Arithmetic table alone: its 18-column range-check logUp (arithmetic_stark.rs:269-276) plus the CPU-facing CTL
+            // rows (arithmetic_stark.rs:61-116) looked up by themselves.
+            s.kinds = {T_ARITHMETIC};
+            TableWithColumns rows = arithmetic::ctl_arithmetic_rows(0);
+            s.ctls.push_back(self_ctl(0, rows.columns, rows.filter));
+            return s;
+        }
         case SYSTEM_MINI3: {
             // tables: 0 = Poseidon, 1 = Logic, 2 = Memory
             s.kinds = {T_POSEIDON, T_LOGIC, T_MEMORY};

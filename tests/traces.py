@@ -5,8 +5,8 @@ poseidon/poseidon_stark.rs:105-145 (via the oracle's orc_gen_poseidon_rows)."""
 import numpy as np
 
 P = 0xFFFFFFFF00000001
-SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH = 0, 1, 2, 3, 4, 5
-T_ARITHMETIC, T_POSEIDON, T_LOGIC, T_MEMORY = 0, 2, 10, 11
+SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK = 0, 1, 2, 3, 4, 5, 6
+T_ARITHMETIC, T_POSEIDON, T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY = 0, 2, 4, 5, 10, 11
 
 
 def logic_trace(log_n: int, seed: int = 1, used_frac: float = 0.8) -> np.ndarray:
@@ -100,3 +100,85 @@ def arithmetic_trace(count: int = 30000, seed: int = 11, log_n: int = 16) -> np.
     """(54, 2^16) uint64: `count` random operations of all 26 kinds (tests/arith_gen.py)."""
     import arith_gen as ag
     return ag.arithmetic_trace(ag.random_ops(count, seed), log_n)
+
+
+def logic_trace_from_ops(ops, log_n: int) -> np.ndarray:
+    """ops = [(kind 0..3 = AND/OR/XOR/NOR, x, y)] -> (69, n); unused rows are all-zero (logic.rs:140-183)."""
+    n = 1 << log_n
+    assert len(ops) <= n
+    t = np.zeros((69, n), dtype=np.uint64)
+    for r, (k, x, y) in enumerate(ops):
+        t[k, r] = 1
+        for i in range(32):
+            t[4 + i, r] = (x >> i) & 1
+            t[36 + i, r] = (y >> i) & 1
+        t[68, r] = [x & y, x | y, x ^ y, (~(x | y)) & 0xFFFFFFFF][k]
+    return t
+
+
+def memory_trace_from_ops(ops, log_n: int) -> np.ndarray:
+    """ops = [(ctx, seg, virt, timestamp, is_read, value)], consistent (reads return the last written value or the
+    first value seen) -> (13, n): sorted by (ctx, seg, virt, timestamp), first-change flags, range check, counter,
+    frequencies, padded by repeating the last operation as a filtered-off read (memory_stark.rs:44-244)."""
+    n = 1 << log_n
+    ops = sorted(ops, key=lambda o: (o[0], o[1], o[2], o[3]))
+    used = len(ops)
+    assert 1 <= used <= n
+    t = np.zeros((13, n), dtype=np.uint64)
+    a = np.array(ops, dtype=np.uint64).T
+    t[0, :used] = 1
+    t[3, :used], t[4, :used], t[5, :used], t[1, :used], t[2, :used], t[6, :used] = a[0], a[1], a[2], a[3], a[4], a[5]
+    for c in (1, 3, 4, 5, 6):
+        t[c, used:] = t[c, used - 1]
+    t[2, used:] = 1
+    o = t.astype(object)
+    for i in range(n - 1):
+        cfc = o[3, i] != o[3, i + 1]
+        sfc = (o[4, i] != o[4, i + 1]) and not cfc
+        vfc = (o[5, i] != o[5, i + 1]) and not sfc and not cfc
+        t[7, i], t[8, i], t[9, i] = int(cfc), int(sfc), int(vfc)
+        rc = (o[3, i + 1] - o[3, i] - 1) if cfc else (o[4, i + 1] - o[4, i] - 1) if sfc else (o[5, i + 1] - o[5, i] - 1) if vfc \
+            else (o[1, i + 1] - o[1, i])
+        assert 0 <= rc < n, rc
+        t[10, i] = rc
+    t[11] = np.arange(n, dtype=np.uint64)
+    t[12] = np.bincount(t[10].astype(np.int64), minlength=n).astype(np.uint64)
+    return t
+
+
+def keccak_system_traces(lens=(0, 4, 132, 136, 272, 140), seed: int = 22):
+    """Keccak slice of AllStark: sponge operations over inputs of the given byte lengths; the permutation, XOR and
+    memory-read rows the sponge rows refer to are derived from them, as witness generation does upstream
+    (witness/operation.rs keccak_general -> KeccakSpongeOp, logic ops, memory reads)."""
+    import hash_gen as hg
+    rng = np.random.default_rng(seed)
+    ops, base = [], 64
+    for i, ln in enumerate(lens):
+        data = bytes(int(b) for b in rng.integers(0, 256, size=ln))
+        nwords = ln // 4 + 1
+        ops.append(([base + 4 * k for k in range(nwords)], 100 + i, data, 0, 0))
+        base += 4 * nwords + 8
+    sponge_rows = sum(len(o[2]) // hg.RATE_BYTES + 1 for o in ops)
+    sponge, perms = hg.keccak_sponge_trace(ops, max(6, (sponge_rows - 1).bit_length()))
+    keccak_in = []
+    for pre, _post, ts in perms:
+        lanes = [pre[2 * k] | (pre[2 * k + 1] << 32) for k in range(25)]
+        keccak_in.append((lanes, ts))
+    keccak = hg.keccak_trace(keccak_in, max(6, (len(keccak_in) * 24 - 1).bit_length()))
+    xors, reads = [], []
+    for r in range(sponge_rows):
+        row = sponge[:, r]
+        ts = int(row[hg.KS_TIMESTAMP])
+        blk = [int(b) for b in row[hg.KS_BLOCK_BYTES:hg.KS_BLOCK_BYTES + hg.RATE_BYTES]]
+        words = [blk[4 * k] | (blk[4 * k + 1] << 8) | (blk[4 * k + 2] << 16) | (blk[4 * k + 3] << 24) for k in range(hg.RATE_U32S)]
+        for k in range(hg.RATE_U32S):
+            xors.append((2, int(row[hg.KS_ORIG_RATE + k]), words[k]))
+        final_len = [int(v) for v in row[hg.KS_IS_FINAL_LEN:hg.KS_IS_FINAL_LEN + hg.RATE_BYTES]]
+        nbytes = hg.RATE_BYTES if int(row[hg.KS_IS_FULL]) else final_len.index(1)
+        for i in range(nbytes):
+            w = i // 4       # MIPS memory words are big-endian: ctl_looking_memory packs bytes [3, 2, 1, 0] little-endian
+            be = (blk[4 * w] << 24) | (blk[4 * w + 1] << 16) | (blk[4 * w + 2] << 8) | blk[4 * w + 3]
+            reads.append((0, 0, int(row[hg.KS_VIRT + w]), ts, 1, be))
+    logic = logic_trace_from_ops(xors, max(6, (len(xors) - 1).bit_length()))
+    memory = memory_trace_from_ops(reads, max(6, (len(reads) - 1).bit_length()))
+    return [keccak, sponge, logic, memory]

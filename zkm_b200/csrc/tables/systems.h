@@ -8,7 +8,7 @@
 namespace zkm {
 namespace tables {
 
-enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5 };
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6 };
 
 // A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
 inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
@@ -42,6 +42,26 @@ inline System make_system(int id) {
             s.kinds = {T_ARITHMETIC};
             TableWithColumns rows = arithmetic::ctl_arithmetic_rows(0);
             s.ctls.push_back(self_ctl(0, rows.columns, rows.filter));
+            return s;
+        }
+        case SYSTEM_KECCAK: {
+            // The Keccak slice of AllStark with its real CTLs (all_stark.rs:216-256,356-386,479-542 restricted to these
+            // tables): 0 = Keccak, 1 = KeccakSponge, 2 = Logic, 3 = Memory.  The sponge's absorbed blocks go through the
+            // permutation table (inputs, outputs), its 34 XORs per row through Logic, its 136 byte reads through Memory;
+            // the CPU-facing sponge output rows are looked up by themselves.
+            s.kinds = {T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY};
+            CrossTableLookup in, out, lg, mem;
+            in.looking_tables.push_back(TableWithColumns(1, keccak_sponge::ctl_looking_keccak_inputs(), keccak_sponge::ctl_looking_keccak_filter()));
+            in.looked_table = TableWithColumns(0, keccak::ctl_data_inputs(), keccak::ctl_filter_inputs());
+            out.looking_tables.push_back(TableWithColumns(1, keccak_sponge::ctl_looking_keccak_outputs(), keccak_sponge::ctl_looking_keccak_filter()));
+            out.looked_table = TableWithColumns(0, keccak::ctl_data_outputs(), keccak::ctl_filter_outputs());
+            for (int i = 0; i < keccak_sponge::num_logic_ctls(); i++)
+                lg.looking_tables.push_back(TableWithColumns(1, keccak_sponge::ctl_looking_logic(i), keccak_sponge::ctl_looking_logic_filter()));
+            lg.looked_table = TableWithColumns(2, logic::ctl_data(), logic::ctl_filter());
+            for (int i = 0; i < keccak_sponge::KECCAK_RATE_BYTES; i++)
+                mem.looking_tables.push_back(TableWithColumns(1, keccak_sponge::ctl_looking_memory(i), keccak_sponge::ctl_looking_memory_filter(i)));
+            mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
+            s.ctls = {in, out, lg, mem, self_ctl(1, keccak_sponge::ctl_looked_data(), keccak_sponge::ctl_looked_filter())};
             return s;
         }
         case SYSTEM_MINI3: {

@@ -218,3 +218,81 @@ def keccak256(data):
     _, perms = keccak_sponge_rows_for_op(([0] * (len(data) // 4 + 2), 0, data, 0, 0))
     post = perms[-1][1]
     return b"".join(int(w).to_bytes(4, "little") for w in post[:8])
+
+
+# ------------------------------------------------------------------------------------- PoseidonSponge
+# poseidon_sponge/poseidon_sponge_stark.rs:187-365 + poseidon_sponge/columns.rs:19-68.  State elements are field
+# elements; every block OVERWRITES the rate (new_rate = the block's 8 little-endian u32s), no xor.
+PS_RATE, PS_CAP, PS_WIDTH, PS_DIGEST, PS_RATE_BYTES = 8, 4, 12, 4, 32
+PS_IS_FULL, PS_CONTEXT, PS_SEGMENT, PS_VIRT = 0, 1, 2, 3
+PS_TIMESTAMP = PS_VIRT + PS_RATE
+PS_LEN = PS_TIMESTAMP + 1
+PS_ALREADY = PS_LEN + 1
+PS_IS_FINAL_LEN = PS_ALREADY + 1
+PS_ORIG_RATE = PS_IS_FINAL_LEN + PS_RATE_BYTES
+PS_ORIG_CAP = PS_ORIG_RATE + PS_RATE
+PS_BLOCK_BYTES = PS_ORIG_CAP + PS_CAP
+PS_NEW_RATE = PS_BLOCK_BYTES + PS_RATE_BYTES
+PS_PARTIAL_UPDATED = PS_NEW_RATE + PS_RATE
+PS_UPDATED_DIGEST = PS_PARTIAL_UPDATED + (PS_WIDTH - PS_DIGEST)
+POSEIDON_SPONGE_COLUMNS = PS_UPDATED_DIGEST + PS_DIGEST
+assert POSEIDON_SPONGE_COLUMNS == 110
+
+
+def poseidon_sponge_rows_for_op(orc, op):
+    """op = (virt of every input word, timestamp, input bytes, context, segment).  Returns rows and, per row, the
+    permutation (input state, output state)."""
+    from oracle.binding import u64ptr
+    virts, ts, data, ctx, seg = op
+    rows, perms = [], []
+    state = [0] * PS_WIDTH
+    nfull = len(data) // PS_RATE_BYTES
+    for b in range(nfull + 1):
+        already = b * PS_RATE_BYTES
+        row = np.zeros(POSEIDON_SPONGE_COLUMNS, dtype=np.uint64)
+        chunk = data[already:already + PS_RATE_BYTES]
+        if b < nfull:
+            row[PS_IS_FULL] = 1
+            row[PS_BLOCK_BYTES:PS_BLOCK_BYTES + PS_RATE_BYTES] = list(chunk)
+        else:
+            row[PS_BLOCK_BYTES:PS_BLOCK_BYTES + len(chunk)] = list(chunk)
+            if len(chunk) == PS_RATE_BYTES - 1:
+                row[PS_BLOCK_BYTES + len(chunk)] = 0b10000001
+            else:
+                row[PS_BLOCK_BYTES + len(chunk)] = 1
+                row[PS_BLOCK_BYTES + PS_RATE_BYTES - 1] = 0b10000000
+            row[PS_IS_FINAL_LEN + len(chunk)] = 1
+        idx = already // 4
+        end = min((already + PS_RATE_BYTES) // 4, len(virts))
+        v = list(virts[idx:end]) + [0] * (PS_RATE - max(0, end - idx))
+        row[PS_CONTEXT], row[PS_SEGMENT] = ctx, seg
+        row[PS_VIRT:PS_VIRT + PS_RATE] = v[:PS_RATE]
+        row[PS_TIMESTAMP], row[PS_LEN], row[PS_ALREADY] = ts, len(data), already
+        row[PS_ORIG_RATE:PS_ORIG_RATE + PS_RATE] = state[:PS_RATE]
+        row[PS_ORIG_CAP:PS_ORIG_CAP + PS_CAP] = state[PS_RATE:]
+        blk = [int(x) for x in row[PS_BLOCK_BYTES:PS_BLOCK_BYTES + PS_RATE_BYTES]]
+        words = [blk[4 * i] | (blk[4 * i + 1] << 8) | (blk[4 * i + 2] << 16) | (blk[4 * i + 3] << 24) for i in range(PS_RATE)]
+        row[PS_NEW_RATE:PS_NEW_RATE + PS_RATE] = words
+        pre = words + state[PS_RATE:]
+        st = np.array(pre, dtype=np.uint64)
+        orc.orc_poseidon_permute(u64ptr(st), 0)
+        state = [int(x) for x in st]
+        row[PS_PARTIAL_UPDATED:PS_PARTIAL_UPDATED + PS_WIDTH - PS_DIGEST] = state[PS_DIGEST:]
+        row[PS_UPDATED_DIGEST:PS_UPDATED_DIGEST + PS_DIGEST] = state[:PS_DIGEST]
+        perms.append((pre, list(state)))
+        rows.append(row)
+    return rows, perms
+
+
+def poseidon_sponge_trace(orc, ops, log_n):
+    rows, perms = [], []
+    for op in ops:
+        r, p = poseidon_sponge_rows_for_op(orc, op)
+        rows += r
+        perms += [(pre, post, op[1]) for pre, post in p]
+    n = 1 << log_n
+    assert len(rows) <= n
+    t = np.zeros((n, POSEIDON_SPONGE_COLUMNS), dtype=np.uint64)
+    if rows:
+        t[:len(rows)] = np.array(rows)
+    return np.ascontiguousarray(t.T), perms

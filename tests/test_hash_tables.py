@@ -104,3 +104,34 @@ def test_keccak_system_rejects_broken_lookups(orc, keccak_traces, which):
         assert _check(orc, kind, t) == 0
     proof = binding.prove_system(orc, tr.SYSTEM_KECCAK, ts)
     assert binding.verify_system(orc, tr.SYSTEM_KECCAK, proof) is not None
+
+
+# ------------------------------------------------------------------------------------------ Poseidon slice
+@pytest.fixture(scope="module")
+def poseidon_traces(orc):
+    return tr.poseidon_system_traces(orc)
+
+
+def test_poseidon_sponge_trace_satisfies_constraints(orc, poseidon_traces):
+    t = poseidon_traces[1]
+    assert t.shape[0] == hg.POSEIDON_SPONGE_COLUMNS
+    assert _check(orc, tr.T_POSEIDON_SPONGE, t) == 0, orc.orc_last_error()
+    # rows: lens (0, 4, 28, 32, 64, 36, 100) -> final rows 0, 1, 2, 4, 7, 9, 13; full rows 3, 5, 6, 8, 10, 11, 12
+    for col, r in ((hg.PS_ALREADY, 4), (hg.PS_LEN, 4), (hg.PS_IS_FULL, 1), (hg.PS_ORIG_RATE + 3, 5), (hg.PS_ORIG_CAP + 1, 6),
+                   (hg.PS_TIMESTAMP, 4), (hg.PS_UPDATED_DIGEST + 2, 5), (hg.PS_PARTIAL_UPDATED + 7, 5)):
+        t2 = t.copy()
+        t2[col, r] = (int(t2[col, r]) + 1) % tr.P
+        assert _check(orc, tr.T_POSEIDON_SPONGE, t2) >= 1, f"column {col} row {r}: corruption accepted"
+
+
+def test_poseidon_system_proves_and_verifies(orc, poseidon_traces):
+    for kind, t in zip((tr.T_POSEIDON, tr.T_POSEIDON_SPONGE, tr.T_MEMORY), poseidon_traces):
+        assert _check(orc, kind, t) == 0
+    proof = binding.prove_system(orc, tr.SYSTEM_POSEIDON_SPONGE, poseidon_traces)
+    assert binding.verify_system(orc, tr.SYSTEM_POSEIDON_SPONGE, proof) is None
+    # a block byte the memory table never served
+    ts = [t.copy() for t in poseidon_traces]
+    ts[1][hg.PS_BLOCK_BYTES + 1, 1] ^= 1
+    ts[1][hg.PS_NEW_RATE, 1] ^= 1 << 8
+    bad = binding.prove_system(orc, tr.SYSTEM_POSEIDON_SPONGE, ts)
+    assert binding.verify_system(orc, tr.SYSTEM_POSEIDON_SPONGE, bad) is not None

@@ -5,8 +5,8 @@ poseidon/poseidon_stark.rs:105-145 (via the oracle's orc_gen_poseidon_rows)."""
 import numpy as np
 
 P = 0xFFFFFFFF00000001
-SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK = 0, 1, 2, 3, 4, 5, 6
-T_ARITHMETIC, T_POSEIDON, T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY = 0, 2, 4, 5, 10, 11
+SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK, SYSTEM_POSEIDON_SPONGE = 0, 1, 2, 3, 4, 5, 6, 7
+T_ARITHMETIC, T_POSEIDON, T_POSEIDON_SPONGE, T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY = 0, 2, 3, 4, 5, 10, 11
 
 
 def logic_trace(log_n: int, seed: int = 1, used_frac: float = 0.8) -> np.ndarray:
@@ -182,3 +182,39 @@ def keccak_system_traces(lens=(0, 4, 132, 136, 272, 140), seed: int = 22):
     logic = logic_trace_from_ops(xors, max(6, (len(xors) - 1).bit_length()))
     memory = memory_trace_from_ops(reads, max(6, (len(reads) - 1).bit_length()))
     return [keccak, sponge, logic, memory]
+
+
+def poseidon_system_traces(orc, lens=(0, 4, 28, 32, 64, 36, 100), seed: int = 23):
+    """Poseidon slice of AllStark: sponge operations, the permutation rows and memory reads they refer to."""
+    import hash_gen as hg
+    from oracle.binding import u64ptr
+    rng = np.random.default_rng(seed)
+    ops, base = [], 64
+    for i, ln in enumerate(lens):
+        data = bytes(int(b) for b in rng.integers(0, 256, size=ln))
+        nwords = ln // 4 + 1
+        ops.append(([base + 4 * k for k in range(nwords)], 200 + i, data, 0, 0))
+        base += 4 * nwords + 8
+    nrows = sum(len(o[2]) // hg.PS_RATE_BYTES + 1 for o in ops)
+    sponge, perms = hg.poseidon_sponge_trace(orc, ops, max(6, (nrows - 1).bit_length()))
+    n_p = 1 << max(6, (len(perms) - 1).bit_length())
+    inputs = np.zeros((n_p, 12), dtype=np.uint64)
+    tsv = np.zeros(n_p, dtype=np.uint64)
+    for k, (pre, _post, ts) in enumerate(perms):
+        inputs[k] = pre
+        tsv[k] = ts
+    rows = np.zeros((n_p, 262), dtype=np.uint64)
+    orc.orc_gen_poseidon_rows(u64ptr(inputs), u64ptr(tsv), n_p, u64ptr(rows))
+    rows[len(perms):, 0] = 0
+    reads = []
+    for r in range(nrows):
+        row = sponge[:, r]
+        blk = [int(b) for b in row[hg.PS_BLOCK_BYTES:hg.PS_BLOCK_BYTES + hg.PS_RATE_BYTES]]
+        final_len = [int(v) for v in row[hg.PS_IS_FINAL_LEN:hg.PS_IS_FINAL_LEN + hg.PS_RATE_BYTES]]
+        nbytes = hg.PS_RATE_BYTES if int(row[hg.PS_IS_FULL]) else final_len.index(1)
+        for i in range(nbytes):
+            w = i // 4
+            be = (blk[4 * w] << 24) | (blk[4 * w + 1] << 16) | (blk[4 * w + 2] << 8) | blk[4 * w + 3]
+            reads.append((0, 0, int(row[hg.PS_VIRT + w]), int(row[hg.PS_TIMESTAMP]), 1, be))
+    memory = memory_trace_from_ops(reads, max(6, (len(reads) - 1).bit_length()))
+    return [np.ascontiguousarray(rows.T), sponge, memory]

@@ -8,7 +8,7 @@
 namespace zkm {
 namespace tables {
 
-enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6 };
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6, SYSTEM_POSEIDON_SPONGE = 7 };
 
 // A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
 inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
@@ -62,6 +62,20 @@ inline System make_system(int id) {
                 mem.looking_tables.push_back(TableWithColumns(1, keccak_sponge::ctl_looking_memory(i), keccak_sponge::ctl_looking_memory_filter(i)));
             mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
             s.ctls = {in, out, lg, mem, self_ctl(1, keccak_sponge::ctl_looked_data(), keccak_sponge::ctl_looked_filter())};
+            return s;
+        }
+        case SYSTEM_POSEIDON_SPONGE: {
+            // The Poseidon slice of AllStark (all_stark.rs:169-211,479-542): 0 = Poseidon, 1 = PoseidonSponge, 2 = Memory.
+            s.kinds = {T_POSEIDON, T_POSEIDON_SPONGE, T_MEMORY};
+            CrossTableLookup in, out, mem;
+            in.looking_tables.push_back(TableWithColumns(1, poseidon_sponge::ctl_looking_poseidon_inputs(), poseidon_sponge::ctl_looking_poseidon_filter()));
+            in.looked_table = TableWithColumns(0, poseidon::ctl_data_inputs(), poseidon::ctl_filter_inputs());
+            out.looking_tables.push_back(TableWithColumns(1, poseidon_sponge::ctl_looking_poseidon_outputs(), poseidon_sponge::ctl_looking_poseidon_filter()));
+            out.looked_table = TableWithColumns(0, poseidon::ctl_data_outputs(), poseidon::ctl_filter_outputs());
+            for (int i = 0; i < poseidon_sponge::POSEIDON_RATE_BYTES; i++)
+                mem.looking_tables.push_back(TableWithColumns(1, poseidon_sponge::ctl_looking_memory(i), poseidon_sponge::ctl_looking_memory_filter(i)));
+            mem.looked_table = TableWithColumns(2, memory::ctl_data(), memory::ctl_filter());
+            s.ctls = {in, out, mem, self_ctl(1, poseidon_sponge::ctl_looked_data(), poseidon_sponge::ctl_looked_filter())};
             return s;
         }
         case SYSTEM_MINI3: {

@@ -26,6 +26,10 @@ def _traces(orc, sid, scale=0):
         return tr.keccak_system_traces()
     if sid == tr.SYSTEM_POSEIDON_SPONGE:
         return tr.poseidon_system_traces(orc)
+    if sid == tr.SYSTEM_SHA_EXTEND:
+        return tr.sha_extend_system_traces()
+    if sid == tr.SYSTEM_SHA_COMPRESS:
+        return tr.sha_compress_system_traces()
     return [tr.poseidon_trace(orc, 6 + scale), tr.logic_trace(8 + scale), tr.memory_trace(7 + scale)]
 
 
@@ -36,7 +40,8 @@ def _first_diff(a, b):
     return None if d.size == 0 else f"first differing word {d[0]} of {a.size} ({d.size} differ)"
 
 
-@pytest.mark.parametrize("sid", [tr.SYSTEM_LOGIC, tr.SYSTEM_POSEIDON, tr.SYSTEM_MEMORY, tr.SYSTEM_MINI3, tr.SYSTEM_ARITH, tr.SYSTEM_KECCAK, tr.SYSTEM_POSEIDON_SPONGE])
+@pytest.mark.parametrize("sid", [tr.SYSTEM_LOGIC, tr.SYSTEM_POSEIDON, tr.SYSTEM_MEMORY, tr.SYSTEM_MINI3, tr.SYSTEM_ARITH, tr.SYSTEM_KECCAK, tr.SYSTEM_POSEIDON_SPONGE,
+                                 tr.SYSTEM_SHA_EXTEND, tr.SYSTEM_SHA_COMPRESS])
 def test_gpu_proof_equals_oracle_proof_and_verifies(zkm, orc, sid):
     traces = _traces(orc, sid)
     gpu = zl.prove_system(zkm, sid, traces)

@@ -5,7 +5,8 @@ poseidon/poseidon_stark.rs:105-145 (via the oracle's orc_gen_poseidon_rows)."""
 import numpy as np
 
 P = 0xFFFFFFFF00000001
-SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK, SYSTEM_POSEIDON_SPONGE = 0, 1, 2, 3, 4, 5, 6, 7
+SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK, SYSTEM_POSEIDON_SPONGE, SYSTEM_SHA_EXTEND, SYSTEM_SHA_COMPRESS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+T_SHA_EXTEND, T_SHA_EXTEND_SPONGE, T_SHA_COMPRESS, T_SHA_COMPRESS_SPONGE = 6, 7, 8, 9
 T_ARITHMETIC, T_POSEIDON, T_POSEIDON_SPONGE, T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY = 0, 2, 3, 4, 5, 10, 11
 
 
@@ -117,7 +118,7 @@ def logic_trace_from_ops(ops, log_n: int) -> np.ndarray:
 
 
 def memory_trace_from_ops(ops, log_n: int) -> np.ndarray:
-    """ops = [(ctx, seg, virt, timestamp, is_read, value)], consistent (reads return the last written value or the
+    """ops = [(ctx, seg, virt, timestamp, is_read, value[, filter = 1])], consistent (reads return the last written value or the
     first value seen) -> (13, n): sorted by (ctx, seg, virt, timestamp), first-change flags, range check, counter,
     frequencies, padded by repeating the last operation as a filtered-off read (memory_stark.rs:44-244)."""
     n = 1 << log_n
@@ -125,8 +126,8 @@ def memory_trace_from_ops(ops, log_n: int) -> np.ndarray:
     used = len(ops)
     assert 1 <= used <= n
     t = np.zeros((13, n), dtype=np.uint64)
-    a = np.array(ops, dtype=np.uint64).T
-    t[0, :used] = 1
+    t[0, :used] = [o[6] if len(o) > 6 else 1 for o in ops]
+    a = np.array([o[:6] for o in ops], dtype=np.uint64).T
     t[3, :used], t[4, :used], t[5, :used], t[1, :used], t[2, :used], t[6, :used] = a[0], a[1], a[2], a[3], a[4], a[5]
     for c in (1, 3, 4, 5, 6):
         t[c, used:] = t[c, used - 1]
@@ -218,3 +219,23 @@ def poseidon_system_traces(orc, lens=(0, 4, 28, 32, 64, 36, 100), seed: int = 23
             reads.append((0, 0, int(row[hg.PS_VIRT + w]), int(row[hg.PS_TIMESTAMP]), 1, be))
     memory = memory_trace_from_ops(reads, max(6, (len(reads) - 1).bit_length()))
     return [np.ascontiguousarray(rows.T), sponge, memory]
+
+
+def sha_extend_system_traces(seqs=((64, 1000), (1024, 5000)), seed: int = 31):
+    """SHA-256 message-schedule slice of AllStark: 48 rounds per sequence, their XORs and memory traffic."""
+    import hash_gen as hg
+    ext, sp, xors, mem = hg.sha_extend_sequences(seqs, seed)
+    lg = lambda k: max(6, (k - 1).bit_length())
+    mem = [m + ((1,) if m[4] else (0,)) for m in mem]        # the CPU's writes carry filter 0 here: no looker in this slice
+    return [hg.rows_to_trace(ext, hg.SHA_EXTEND_COLUMNS, lg(len(ext))), hg.rows_to_trace(sp, hg.SHA_EXTEND_SPONGE_COLUMNS, lg(len(sp))),
+            logic_trace_from_ops(xors, lg(len(xors))), memory_trace_from_ops(mem, lg(len(mem)))]
+
+
+def sha_compress_system_traces(calls=((64, 128, 3000), (512, 576, 7000)), seed: int = 41):
+    """SHA-256 compression slice of AllStark: 65 rows per compression, 12 logic operations and one message-word read
+    per round, the chaining-value reads of the sponge row."""
+    import hash_gen as hg
+    c, sp, logic, mem, _ = hg.sha_compressions(calls, seed)
+    lg = lambda k: max(6, (k - 1).bit_length())
+    return [hg.rows_to_trace(c, hg.SHA_COMPRESS_COLUMNS, lg(len(c))), hg.rows_to_trace(sp, hg.SHA_COMPRESS_SPONGE_COLUMNS, lg(len(sp))),
+            logic_trace_from_ops(logic, lg(len(logic))), memory_trace_from_ops(mem, lg(len(mem)))]

@@ -8,7 +8,7 @@
 namespace zkm {
 namespace tables {
 
-enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6, SYSTEM_POSEIDON_SPONGE = 7 };
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6, SYSTEM_POSEIDON_SPONGE = 7, SYSTEM_SHA_EXTEND = 8, SYSTEM_SHA_COMPRESS = 9 };
 
 // A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
 inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
@@ -76,6 +76,49 @@ inline System make_system(int id) {
                 mem.looking_tables.push_back(TableWithColumns(1, poseidon_sponge::ctl_looking_memory(i), poseidon_sponge::ctl_looking_memory_filter(i)));
             mem.looked_table = TableWithColumns(2, memory::ctl_data(), memory::ctl_filter());
             s.ctls = {in, out, mem, self_ctl(1, poseidon_sponge::ctl_looked_data(), poseidon_sponge::ctl_looked_filter())};
+            return s;
+        }
+        case SYSTEM_SHA_EXTEND: {
+            // The SHA-256 message-schedule slice of AllStark (all_stark.rs:258-298,356-386,479-542):
+            // 0 = ShaExtend, 1 = ShaExtendSponge, 2 = Logic, 3 = Memory.
+            s.kinds = {T_SHA_EXTEND, T_SHA_EXTEND_SPONGE, T_LOGIC, T_MEMORY};
+            CrossTableLookup in, out, lg, mem;
+            in.looking_tables.push_back(TableWithColumns(1, sha_extend_sponge::ctl_looking_sha_extend_inputs(), sha_extend_sponge::ctl_looking_sha_extend_filter()));
+            in.looked_table = TableWithColumns(0, sha_extend::ctl_data_inputs(), sha_extend::ctl_filter());
+            out.looking_tables.push_back(TableWithColumns(1, sha_extend_sponge::ctl_looking_sha_extend_outputs(), sha_extend_sponge::ctl_looking_sha_extend_filter()));
+            out.looked_table = TableWithColumns(0, sha_extend::ctl_data_outputs(), sha_extend::ctl_filter());
+            lg.looking_tables = {TableWithColumns(0, sha_extend::ctl_s_0_inter_looking_logic(), sha_extend::ctl_filter()),
+                                 TableWithColumns(0, sha_extend::ctl_s_0_looking_logic(), sha_extend::ctl_filter()),
+                                 TableWithColumns(0, sha_extend::ctl_s_1_inter_looking_logic(), sha_extend::ctl_filter()),
+                                 TableWithColumns(0, sha_extend::ctl_s_1_looking_logic(), sha_extend::ctl_filter())};
+            lg.looked_table = TableWithColumns(2, logic::ctl_data(), logic::ctl_filter());
+            for (int i = 0; i < sha_extend_sponge::SHA_EXTEND_SPONGE_READ_BYTES; i++)
+                mem.looking_tables.push_back(TableWithColumns(1, sha_extend_sponge::ctl_looking_memory(i), sha_extend_sponge::ctl_looking_sha_extend_filter()));
+            mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
+            s.ctls = {in, out, lg, mem, self_ctl(1, sha_extend_sponge::ctl_looked_data(), sha_extend_sponge::ctl_looking_sha_extend_filter())};
+            return s;
+        }
+        case SYSTEM_SHA_COMPRESS: {
+            // The SHA-256 compression slice of AllStark (all_stark.rs:300-340,356-386,479-542):
+            // 0 = ShaCompress, 1 = ShaCompressSponge, 2 = Logic, 3 = Memory.
+            s.kinds = {T_SHA_COMPRESS, T_SHA_COMPRESS_SPONGE, T_LOGIC, T_MEMORY};
+            CrossTableLookup in, out, lg, mem;
+            in.looking_tables.push_back(TableWithColumns(1, sha_compress_sponge::ctl_looking_sha_compress_inputs(), sha_compress_sponge::ctl_looking_sha_compress_filter()));
+            in.looked_table = TableWithColumns(0, sha_compress::ctl_data_inputs(), sha_compress::ctl_filter_inputs());
+            out.looking_tables.push_back(TableWithColumns(1, sha_compress_sponge::ctl_looking_sha_compress_outputs(), sha_compress_sponge::ctl_looking_sha_compress_filter()));
+            out.looked_table = TableWithColumns(0, sha_compress::ctl_data_outputs(), sha_compress::ctl_filter_outputs());
+            typedef std::vector<Column> (*colfn)();
+            const colfn sc[12] = {sha_compress::ctl_s_1_inter_looking_logic, sha_compress::ctl_s_1_looking_logic, sha_compress::ctl_e_and_f_looking_logic,
+                                  sha_compress::ctl_not_e_and_g_looking_logic, sha_compress::ctl_ch_looking_logic, sha_compress::ctl_s_0_inter_looking_logic,
+                                  sha_compress::ctl_s_0_looking_logic, sha_compress::ctl_a_and_b_looking_logic, sha_compress::ctl_a_and_c_looking_logic,
+                                  sha_compress::ctl_b_and_c_looking_logic, sha_compress::ctl_maj_inter_looking_logic, sha_compress::ctl_maj_looking_logic};
+            for (colfn f : sc) lg.looking_tables.push_back(TableWithColumns(0, f(), sha_compress::ctl_logic_filter()));
+            lg.looked_table = TableWithColumns(2, logic::ctl_data(), logic::ctl_filter());
+            for (int i = 0; i < sha_compress_sponge::SHA_COMPRESS_SPONGE_READ_BYTES; i++)
+                mem.looking_tables.push_back(TableWithColumns(1, sha_compress_sponge::ctl_looking_memory(i), sha_compress_sponge::ctl_looking_sha_compress_filter()));
+            for (int i = 0; i < 4; i++) mem.looking_tables.push_back(TableWithColumns(0, sha_compress::ctl_looking_memory(i), sha_compress::ctl_logic_filter()));
+            mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
+            s.ctls = {in, out, lg, mem, self_ctl(1, sha_compress_sponge::ctl_looked_data(), sha_compress_sponge::ctl_looked_filter())};
             return s;
         }
         case SYSTEM_MINI3: {

@@ -30,6 +30,8 @@ def _traces(orc, sid, scale=0):
         return tr.sha_extend_system_traces()
     if sid == tr.SYSTEM_SHA_COMPRESS:
         return tr.sha_compress_system_traces()
+    if sid == tr.SYSTEM_CPU:
+        return tr.cpu_system_traces()
     return [tr.poseidon_trace(orc, 6 + scale), tr.logic_trace(8 + scale), tr.memory_trace(7 + scale)]
 
 
@@ -41,7 +43,7 @@ def _first_diff(a, b):
 
 
 @pytest.mark.parametrize("sid", [tr.SYSTEM_LOGIC, tr.SYSTEM_POSEIDON, tr.SYSTEM_MEMORY, tr.SYSTEM_MINI3, tr.SYSTEM_ARITH, tr.SYSTEM_KECCAK, tr.SYSTEM_POSEIDON_SPONGE,
-                                 tr.SYSTEM_SHA_EXTEND, tr.SYSTEM_SHA_COMPRESS])
+                                 tr.SYSTEM_SHA_EXTEND, tr.SYSTEM_SHA_COMPRESS, tr.SYSTEM_CPU])
 def test_gpu_proof_equals_oracle_proof_and_verifies(zkm, orc, sid):
     traces = _traces(orc, sid)
     gpu = zl.prove_system(zkm, sid, traces)

@@ -5,7 +5,8 @@ poseidon/poseidon_stark.rs:105-145 (via the oracle's orc_gen_poseidon_rows)."""
 import numpy as np
 
 P = 0xFFFFFFFF00000001
-SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK, SYSTEM_POSEIDON_SPONGE, SYSTEM_SHA_EXTEND, SYSTEM_SHA_COMPRESS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+SYSTEM_ALL_STARK, SYSTEM_LOGIC, SYSTEM_MINI3, SYSTEM_POSEIDON, SYSTEM_MEMORY, SYSTEM_ARITH, SYSTEM_KECCAK, SYSTEM_POSEIDON_SPONGE, SYSTEM_SHA_EXTEND, SYSTEM_SHA_COMPRESS, SYSTEM_CPU = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+T_CPU = 1
 T_SHA_EXTEND, T_SHA_EXTEND_SPONGE, T_SHA_COMPRESS, T_SHA_COMPRESS_SPONGE = 6, 7, 8, 9
 T_ARITHMETIC, T_POSEIDON, T_POSEIDON_SPONGE, T_KECCAK, T_KECCAK_SPONGE, T_LOGIC, T_MEMORY = 0, 2, 3, 4, 5, 10, 11
 
@@ -239,3 +240,19 @@ def sha_compress_system_traces(calls=((64, 128, 3000), (512, 576, 7000)), seed: 
     lg = lambda k: max(6, (k - 1).bit_length())
     return [hg.rows_to_trace(c, hg.SHA_COMPRESS_COLUMNS, lg(len(c))), hg.rows_to_trace(sp, hg.SHA_COMPRESS_SPONGE_COLUMNS, lg(len(sp))),
             logic_trace_from_ops(logic, lg(len(logic))), memory_trace_from_ops(mem, lg(len(mem)))]
+
+
+def cpu_system_traces():
+    """Instruction-execution slice of AllStark: the test program of tests/cpu_program.py run by the interpreter of
+    tests/cpu_gen.py; the arithmetic, logic and memory tables are generated from the operations it logged."""
+    import arith_gen as ag
+    import cpu_gen as cg
+    import cpu_program as cp
+    image, end = cp.build()
+    cpu = cg.MiniCpu(image, cp.ENTRY)
+    while cpu.pc != end:
+        cpu.step()
+        assert cpu.clock() < 250
+    lg = lambda k: max(6, (k - 1).bit_length())
+    return [cpu.cpu_trace(8), ag.arithmetic_trace(cpu.arith_ops, 16), logic_trace_from_ops(cpu.logic_ops, lg(len(cpu.logic_ops))),
+            cg.memory_generate_trace(cpu.mem_ops)]

@@ -8,7 +8,7 @@
 namespace zkm {
 namespace tables {
 
-enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6, SYSTEM_POSEIDON_SPONGE = 7, SYSTEM_SHA_EXTEND = 8, SYSTEM_SHA_COMPRESS = 9 };
+enum SystemId { SYSTEM_ALL_STARK = 0, SYSTEM_LOGIC = 1, SYSTEM_MINI3 = 2, SYSTEM_POSEIDON = 3, SYSTEM_MEMORY = 4, SYSTEM_ARITH = 5, SYSTEM_KECCAK = 6, SYSTEM_POSEIDON_SPONGE = 7, SYSTEM_SHA_EXTEND = 8, SYSTEM_SHA_COMPRESS = 9, SYSTEM_CPU = 10 };
 
 // A table looked up by itself: looking = looked (multiset equality holds trivially for any trace).
 inline CrossTableLookup self_ctl(int table, std::vector<Column> cols, Filter f) {
@@ -119,6 +119,20 @@ inline System make_system(int id) {
             for (int i = 0; i < 4; i++) mem.looking_tables.push_back(TableWithColumns(0, sha_compress::ctl_looking_memory(i), sha_compress::ctl_logic_filter()));
             mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
             s.ctls = {in, out, lg, mem, self_ctl(1, sha_compress_sponge::ctl_looked_data(), sha_compress_sponge::ctl_looked_filter())};
+            return s;
+        }
+        case SYSTEM_CPU: {
+            // The instruction-execution slice of AllStark (all_stark.rs:156-164, 340-355, 479-487):
+            // 0 = Cpu, 1 = Arithmetic, 2 = Logic, 3 = Memory with the CPU's arithmetic, logic and 9 memory-channel lookups.
+            s.kinds = {T_CPU, T_ARITHMETIC, T_LOGIC, T_MEMORY};
+            CrossTableLookup ar, lg, mem;
+            ar.looking_tables = {cpu::ctl_arithmetic_base_rows(0), cpu::ctl_arithmetic_imm_base_rows(0)};
+            ar.looked_table = arithmetic::ctl_arithmetic_rows(1);
+            lg.looking_tables = {TableWithColumns(0, cpu::ctl_data_logic(), cpu::ctl_filter_logic())};
+            lg.looked_table = TableWithColumns(2, logic::ctl_data(), logic::ctl_filter());
+            for (int c = 0; c < cpu::NUM_GP_CHANNELS; c++) mem.looking_tables.push_back(TableWithColumns(0, cpu::ctl_data_gp_memory(c), cpu::ctl_filter_gp_memory(c)));
+            mem.looked_table = TableWithColumns(3, memory::ctl_data(), memory::ctl_filter());
+            s.ctls = {ar, lg, mem};
             return s;
         }
         case SYSTEM_MINI3: {

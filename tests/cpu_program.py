@@ -6,7 +6,11 @@ ENTRY, DATA = 0x1000, 0x2000
 SYNC = rtype(0b001111)
 
 
-def build():
+KDATA, KOUT, WDATA, HDATA, IMAGE_ID = 0x2100, 0x2200, 0x2300, 0x2400, 0x2500
+KECCAK_LEN = 140
+
+
+def build(with_syscalls=False):
     p = []
 
     def emit(w):
@@ -100,6 +104,34 @@ def build():
     emit(itype(0b001101, 0, 30, at + 20))
     emit(rtype(0x09, rs=30, rd=29))                     # jalr $29, $30
     emit(SYNC); emit(itype(0b001001, 2, 2, 1)); emit(SYNC)
+    if with_syscalls:
+        def li(reg, v):
+            if v >> 16:
+                emit(itype(0b001111, 0, reg, v >> 16))              # lui
+                emit(itype(0b001101, reg, reg, v & 0xFFFF))         # ori
+            else:
+                emit(itype(0b001101, 0, reg, v))
+
+        def sys(num, a0=0, a1=0, a2=0):
+            li(2, num); li(4, a0); li(5, a1); li(6, a2)
+            emit(rtype(0b001100))                                   # syscall
+        sys(4045, 0x5000)                # brk above the current break
+        sys(4045, 0)                     # brk below
+        sys(4090, 0, 0x2000)             # mmap, aligned size, from the heap
+        sys(4210, 0, 0x1234)             # mmap2, unaligned size
+        sys(4090, 0x7000, 0x1000)        # mmap at a given address
+        sys(4120)                        # clone
+        sys(4003, 0)                     # read stdin
+        sys(4003, 5)                     # read bad fd
+        sys(4004, 1, 0, 17)              # write stdout
+        sys(4004, 7, 0, 17)              # write bad fd
+        sys(4055, 0); sys(4055, 2); sys(4055, 9)   # fcntl
+        sys(4283, 0x1234)                # set_thread_area
+        sys(4999)                        # unknown number
+        sys(0x010109, KDATA, KECCAK_LEN, KOUT)      # keccak precompile
+        sys(0x00300105, WDATA, 0)        # sha extend
+        sys(0x00010106, WDATA, HDATA)    # sha compress
+        emit(itype(0b100011, 28, 15, KOUT - DATA))  # lw: read back the first digest word
     end = ENTRY + 4 * len(p)
     for _ in range(4):
         emit(SYNC)
@@ -108,4 +140,10 @@ def build():
     image[DATA - 4] = 0x0BADF00D
     for i, w in enumerate(data):
         image[DATA + 4 * i] = w
+    if with_syscalls:
+        x = 0x9E3779B9
+        for base, count in ((KDATA, KECCAK_LEN // 4), (WDATA, 16), (HDATA, 8)):
+            for i in range(count):
+                x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+                image[base + 4 * i] = x
     return image, end

@@ -120,3 +120,20 @@ def test_all_stark_synthetic_proof_equals_oracle_mid_heights(zkm, orc):
     gpu = zl.prove_system(zkm, tr.SYSTEM_ALL_STARK, traces)
     cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
     assert _first_diff(gpu, cpu) is None
+
+
+def test_all_stark_valid_trace_proof_verifies(zkm, orc):
+    """The drop-in entry point on a VALID 12-table trace (MIPS program with syscalls and the Keccak / SHA-256 / Poseidon
+    precompiles, tests/traces.py all_stark_valid_traces): the GPU proof is accepted by the restated verifier
+    (verifier.rs logic, all 15 cross-table lookups) and equals the oracle's proof word for word."""
+    traces = tr.all_stark_valid_traces(orc)
+    gpu = zl.prove_with_traces(zkm, traces)
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, gpu) is None
+    cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
+    assert _first_diff(gpu, cpu) is None
+    # a precompile result the sponge table does not back: the GPU proof is rejected like the oracle's
+    import cpu_gen as cg
+    bad = [t.copy() for t in traces]
+    r = int(np.nonzero(bad[1][cg.IS_KECCAK_SPONGE])[0][0])
+    bad[1][cg.GENERAL, r] += 1
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, zl.prove_with_traces(zkm, bad)) is not None

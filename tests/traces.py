@@ -256,3 +256,83 @@ def cpu_system_traces():
     lg = lambda k: max(6, (k - 1).bit_length())
     return [cpu.cpu_trace(8), ag.arithmetic_trace(cpu.arith_ops, 16), logic_trace_from_ops(cpu.logic_ops, lg(len(cpu.logic_ops))),
             cg.memory_generate_trace(cpu.mem_ops)]
+
+
+def all_stark_valid_traces(orc):
+    """A valid trace of all 12 AllStark tables: the test program with its syscalls and the Keccak / SHA-256 precompiles
+    (tests/cpu_program.py, with_syscalls), the image-id Poseidon hash of the bootstrap, and every table generated from
+    the operations the interpreter logged -- what Traces::into_tables does upstream (witness/traces.rs:230-318)."""
+    import arith_gen as ag
+    import cpu_gen as cg
+    import cpu_program as cp
+    import hash_gen as hg
+    from oracle.binding import u64ptr
+    image, end = cp.build(with_syscalls=True)
+    cpu = cg.MiniCpu(image, cp.ENTRY, image_id_words=(cp.IMAGE_ID, [0x01020304 * (k + 1) & 0xFFFFFFFF for k in range(9)]))
+    while cpu.pc != end:
+        cpu.step()
+        assert cpu.clock() < 1000
+    lg = lambda k: max(6, (max(k, 1) - 1).bit_length())
+    # Poseidon sponge + permutations; the digest goes back into the CPU's image-id row
+    ps_rows, ps_perms = [], []
+    for addrs, ts, data, ctx, seg, cpu_row in cpu.poseidon_ops:
+        r, perms = hg.poseidon_sponge_rows_for_op(orc, (addrs, ts, data, ctx, seg))
+        ps_rows += r
+        ps_perms += [(pre, ts) for pre, _ in perms]
+        for k in range(4):
+            cpu_row[cg.GENERAL + k] = perms[-1][1][k]
+    n_p = 1 << lg(len(ps_perms))
+    p_in, p_ts = np.zeros((n_p, 12), dtype=np.uint64), np.zeros(n_p, dtype=np.uint64)
+    for k, (pre, ts) in enumerate(ps_perms):
+        p_in[k], p_ts[k] = pre, ts
+    p_rows = np.zeros((n_p, 262), dtype=np.uint64)
+    orc.orc_gen_poseidon_rows(u64ptr(p_in), u64ptr(p_ts), n_p, u64ptr(p_rows))
+    p_rows[len(ps_perms):, 0] = 0
+    # Keccak sponge + permutations + XORs
+    ks_rows, k_in, logic = [], [], list(cpu.logic_ops)
+    for op in cpu.keccak_ops:
+        r, perms = hg.keccak_sponge_rows_for_op(op)
+        for row, (pre, _post) in zip(r, perms):
+            blk = [int(b) for b in row[hg.KS_BLOCK_BYTES:hg.KS_BLOCK_BYTES + hg.RATE_BYTES]]
+            for k in range(hg.RATE_U32S):
+                logic.append((2, int(row[hg.KS_ORIG_RATE + k]), blk[4 * k] | (blk[4 * k + 1] << 8) | (blk[4 * k + 2] << 16) | (blk[4 * k + 3] << 24)))
+            k_in.append(([pre[2 * k] | (pre[2 * k + 1] << 32) for k in range(25)], op[1]))
+        ks_rows += r
+    # SHA extend / compress tables from the logged calls
+    se_rows, ses_rows = [], []
+    for ins, virts, out_virt, ts, rnd, w_i in cpu.sha_extend_ops:
+        se_rows.append(hg.sha_extend_row(*ins, ts)[0])
+        sp = np.zeros(hg.SHA_EXTEND_SPONGE_COLUMNS, dtype=np.uint64)
+        sp[hg.SES_ROUND + rnd] = 1
+        for at, v in zip((hg.SES_W_M15, hg.SES_W_M2, hg.SES_W_M16, hg.SES_W_M7), ins):
+            sp[at:at + 4] = hg._le4(v)
+        sp[hg.SES_W_I:hg.SES_W_I + 4] = hg._le4(w_i)
+        sp[hg.SES_INPUT_VIRT:hg.SES_INPUT_VIRT + 4], sp[hg.SES_OUTPUT_VIRT], sp[hg.SES_TIMESTAMP] = virts, out_virt, ts
+        ses_rows.append(sp)
+    sc_rows, scs_rows = [], []
+    for hx, w, h_ptr, w_ptr, ts in cpu.sha_compress_ops:
+        st = list(hx)
+        for i in range(64):
+            row, st, _ = hg.sha_compress_row(st, w[i], hg.SHA_K[i], i, w_ptr + 4 * i, ts)
+            sc_rows.append(row)
+        sc_rows.append(hg.sha_compress_row(st, 0, 0, 64, w_ptr + 4 * 64, ts)[0])
+        sp = np.zeros(hg.SHA_COMPRESS_SPONGE_COLUMNS, dtype=np.uint64)
+        sp[hg.SCS_TIMESTAMP], sp[hg.SCS_IS_REAL], sp[hg.SCS_W_START_VIRT] = ts, 1, w_ptr
+        sp[hg.SCS_HX_VIRT:hg.SCS_HX_VIRT + 8] = [h_ptr + 4 * j for j in range(8)]
+        for j in range(8):
+            sp[hg.SCS_HX + 4 * j:hg.SCS_HX + 4 * j + 4] = hg._le4(hx[j])
+            sp[hg.SCS_OUTPUT_STATE + 4 * j:hg.SCS_OUTPUT_STATE + 4 * j + 4] = hg._le4(st[j])
+            hg._wadd(sp, hg.SCS_OUTPUT_HX + 6 * j, 2, hx[j], st[j])
+        scs_rows.append(sp)
+    return [ag.arithmetic_trace(cpu.arith_ops, 16),
+            cpu.cpu_trace(lg(cpu.clock() + 1)),
+            np.ascontiguousarray(p_rows.T),
+            hg.rows_to_trace(ps_rows, hg.POSEIDON_SPONGE_COLUMNS, lg(len(ps_rows))),
+            hg.keccak_trace(k_in, lg(len(k_in) * 24)),
+            hg.rows_to_trace(ks_rows, hg.KECCAK_SPONGE_COLUMNS, lg(len(ks_rows))),
+            hg.rows_to_trace(se_rows, hg.SHA_EXTEND_COLUMNS, lg(len(se_rows))),
+            hg.rows_to_trace(ses_rows, hg.SHA_EXTEND_SPONGE_COLUMNS, lg(len(ses_rows))),
+            hg.rows_to_trace(sc_rows, hg.SHA_COMPRESS_COLUMNS, lg(len(sc_rows))),
+            hg.rows_to_trace(scs_rows, hg.SHA_COMPRESS_SPONGE_COLUMNS, lg(len(scs_rows))),
+            logic_trace_from_ops(logic, lg(len(logic))),
+            cg.memory_generate_trace(cpu.mem_ops)]

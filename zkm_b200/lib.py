@@ -154,6 +154,25 @@ def prove_system(lib, system_id, traces, roots_before=None, roots_after=None, us
     return proof
 
 
+def prove_with_traces(lib, traces, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):
+    """The drop-in entry point (reference prover.rs:130-140 prove_with_traces): 12 host traces in `Table` order
+    -> AllProof buffer."""
+    cfg = cfg or standard_fast_config(lib)
+    assert len(traces) == 12
+    made = [make_table(np.ascontiguousarray(t)) for t in traces]
+    arr = (Table * 12)(*[m[0] for m in made])
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    out = C.POINTER(C.c_uint64)()
+    words = C.c_size_t()
+    err = C.c_void_p()
+    rc = lib.zkm_b200_prove_with_traces(arr, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words), C.byref(err))
+    check(lib, rc, err)
+    proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+    lib.zkm_b200_free(out)
+    return proof
+
+
 def system_shape(lib, system_id):
     n = C.c_uint32()
     nc = (C.c_uint32 * 32)()

@@ -706,21 +706,18 @@ def memory_generate_trace(ops):
     n = 1 << (len(ops) - 1).bit_length()
     ops += [(last[0], last[1], last[2], last[3], 1, last[5], 0)] * (n - len(ops))
     ops = sorted(ops, key=key)
+    a = np.array(ops, dtype=np.int64).T                      # ctx, seg, virt, ts, is_read, value, filter
+    r0 = (a[4] == 0) & (a[0] == 0) & (a[1] == SEG_REGISTER_FILE) & (a[2] == 0)
+    a[5][r0] = 0                                             # into_row :62-72: writes to R0 are recorded as 0
     t = np.zeros((13, n), dtype=np.uint64)
-    for r, (ctx, seg, virt, ts, is_read, value, filt) in enumerate(ops):
-        if not is_read and ctx == 0 and seg == SEG_REGISTER_FILE and virt == 0:
-            value = 0                                        # into_row :62-72: writes to R0 are recorded as 0
-        t[0, r], t[1, r], t[2, r], t[3, r], t[4, r], t[5, r], t[6, r] = filt, ts, is_read, ctx, seg, virt, value
-    o = t.astype(object)
-    for i in range(n - 1):
-        cfc = o[3, i] != o[3, i + 1]
-        sfc = (o[4, i] != o[4, i + 1]) and not cfc
-        vfc = (o[5, i] != o[5, i + 1]) and not sfc and not cfc
-        t[7, i], t[8, i], t[9, i] = int(cfc), int(sfc), int(vfc)
-        rc = (o[3, i + 1] - o[3, i] - 1) if cfc else (o[4, i + 1] - o[4, i] - 1) if sfc else (o[5, i + 1] - o[5, i] - 1) if vfc \
-            else (o[1, i + 1] - o[1, i])
-        assert 0 <= rc < n, f"Range check of {rc} is too large. Bug in fill_gaps?"
-        t[10, i] = rc
+    t[0], t[1], t[2], t[3], t[4], t[5], t[6] = a[6], a[3], a[4], a[0], a[1], a[2], a[5]
+    cfc = a[0][:-1] != a[0][1:]
+    sfc = (a[1][:-1] != a[1][1:]) & ~cfc
+    vfc = (a[2][:-1] != a[2][1:]) & ~sfc & ~cfc
+    rc = np.where(cfc, a[0][1:] - a[0][:-1] - 1, np.where(sfc, a[1][1:] - a[1][:-1] - 1, np.where(vfc, a[2][1:] - a[2][:-1] - 1,
+                                                                                                 a[3][1:] - a[3][:-1])))
+    assert rc.min() >= 0 and rc.max() < n, f"Range check of {rc.max()} is too large. Bug in fill_gaps?"
+    t[7, :-1], t[8, :-1], t[9, :-1], t[10, :-1] = cfc, sfc, vfc, rc
     t[11] = np.arange(n, dtype=np.uint64)
     t[12] = np.bincount(t[10].astype(np.int64), minlength=n).astype(np.uint64)
     return t

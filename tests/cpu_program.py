@@ -10,7 +10,7 @@ KDATA, KOUT, WDATA, HDATA, IMAGE_ID = 0x2100, 0x2200, 0x2300, 0x2400, 0x2500
 KECCAK_LEN = 140
 
 
-def build(with_syscalls=False):
+def build(with_syscalls=False, sha_blocks=0):
     p = []
 
     def emit(w):
@@ -132,6 +132,15 @@ def build(with_syscalls=False):
         sys(0x00300105, WDATA, 0)        # sha extend
         sys(0x00010106, WDATA, HDATA)    # sha compress
         emit(itype(0b100011, 28, 15, KOUT - DATA))  # lw: read back the first digest word
+        if sha_blocks:                   # a "sha2 guest" loop: extend + compress the same block sha_blocks times, chaining hx
+            li(16, sha_blocks)
+            loop = ENTRY + 4 * len(p)
+            sys(0x00300105, WDATA, 0)
+            sys(0x00010106, WDATA, HDATA)
+            emit(itype(0b001001, 16, 16, 0xFFFF))                   # addiu $16, $16, -1
+            at = ENTRY + 4 * len(p)
+            emit(itype(0x05, 16, 0, ((loop - (at + 4)) >> 2) & 0xFFFF))   # bne $16, $0, loop
+            emit(SYNC)                                              # delay slot
     end = ENTRY + 4 * len(p)
     for _ in range(4):
         emit(SYNC)

@@ -137,3 +137,24 @@ def test_all_stark_valid_trace_proof_verifies(zkm, orc):
     r = int(np.nonzero(bad[1][cg.IS_KECCAK_SPONGE])[0][0])
     bad[1][cg.GENERAL, r] += 1
     assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, zl.prove_with_traces(zkm, bad)) is not None
+
+
+def test_sha2_guest_segment_valid_proof(zkm, orc):
+    """BASELINE config 1 analogue (a SHA-256 guest, one 2^16-row segment): the test program followed by a loop of 500
+    sha_extend + sha_compress precompile calls -> CPU table 2^16 rows, Logic 2^19, Memory 2^20, SHA tables 2^15..2^16, all
+    valid.  The GPU proof must be accepted by the restated verifier; at 40 blocks (CPU 2^13) it must also equal the
+    oracle's proof word for word."""
+    small = tr.all_stark_valid_traces(orc, sha_blocks=40)
+    gpu = zl.prove_with_traces(zkm, small)
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, gpu) is None
+    assert _first_diff(gpu, binding.prove_system(orc, tr.SYSTEM_ALL_STARK, small)) is None
+    big = tr.all_stark_valid_traces(orc, sha_blocks=500)
+    heights = [t.shape[1].bit_length() - 1 for t in big]
+    assert heights[1] == 16 and heights[10] == 19 and heights[11] == 20, heights
+    gpu = zl.prove_with_traces(zkm, big)
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, gpu) is None
+    # and a single wrong message-schedule word anywhere in the segment is fatal
+    import cpu_gen as cg
+    rows = np.nonzero(big[1][cg.IS_SHA_EXTEND_SPONGE])[0]
+    big[1][cg.GENERAL, int(rows[len(rows) // 2])] += 1
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, zl.prove_with_traces(zkm, big)) is not None

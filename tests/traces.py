@@ -258,7 +258,7 @@ def cpu_system_traces():
             cg.memory_generate_trace(cpu.mem_ops)]
 
 
-def all_stark_valid_traces(orc):
+def all_stark_valid_traces(orc, sha_blocks=0):
     """A valid trace of all 12 AllStark tables: the test program with its syscalls and the Keccak / SHA-256 precompiles
     (tests/cpu_program.py, with_syscalls), the image-id Poseidon hash of the bootstrap, and every table generated from
     the operations the interpreter logged -- what Traces::into_tables does upstream (witness/traces.rs:230-318)."""
@@ -267,11 +267,11 @@ def all_stark_valid_traces(orc):
     import cpu_program as cp
     import hash_gen as hg
     from oracle.binding import u64ptr
-    image, end = cp.build(with_syscalls=True)
+    image, end = cp.build(with_syscalls=True, sha_blocks=sha_blocks)
     cpu = cg.MiniCpu(image, cp.ENTRY, image_id_words=(cp.IMAGE_ID, [0x01020304 * (k + 1) & 0xFFFFFFFF for k in range(9)]))
     while cpu.pc != end:
         cpu.step()
-        assert cpu.clock() < 1000
+        assert cpu.clock() < 1000 + 200 * sha_blocks
     lg = lambda k: max(6, (max(k, 1) - 1).bit_length())
     # Poseidon sponge + permutations; the digest goes back into the CPU's image-id row
     ps_rows, ps_perms = [], []

@@ -158,3 +158,14 @@ def test_sha2_guest_segment_valid_proof(zkm, orc):
     rows = np.nonzero(big[1][cg.IS_SHA_EXTEND_SPONGE])[0]
     big[1][cg.GENERAL, int(rows[len(rows) // 2])] += 1
     assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, zl.prove_with_traces(zkm, big)) is not None
+
+
+def test_grouped_upload_commit_is_identical(zkm, orc, monkeypatch):
+    """Host tables above a size threshold are uploaded and transformed in 4 column groups (NTTs overlap the upload); the proof
+    must not change.  The threshold is lowered so that the small test tables take that path."""
+    traces = tr.keccak_system_traces()
+    ref = zl.prove_system(zkm, tr.SYSTEM_KECCAK, traces)
+    monkeypatch.setenv("ZKM_GROUP_BYTES", "4096")
+    grouped = zl.prove_system(zkm, tr.SYSTEM_KECCAK, traces)
+    assert _first_diff(ref, grouped) is None
+    assert _first_diff(grouped, binding.prove_system(orc, tr.SYSTEM_KECCAK, traces)) is None

@@ -108,6 +108,31 @@ void batch_from_coeffs_dev(Batch& b, DevBuf&& coeffs, int ncols, int log_n, int 
     commit_lde(b);
 }
 
+void batch_from_values_grouped_dev(Batch& b, const u64* values, DevBuf&& coeffs, int ncols, int log_n, int rate_bits, int cap_height,
+                                   const std::vector<int>& col_ends, const std::function<void(size_t)>& wait_group) {
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    ZKM_CHECK(ncols > 0 && !col_ends.empty() && col_ends.back() == ncols, "bad column groups");
+    ZKM_CHECK(log_n + rate_bits >= cap_height, "cap height exceeds LDE tree height");
+    ZKM_CHECK(log_n + rate_bits <= 31, "LDE too large");
+    b.ncols = ncols; b.log_n = log_n; b.rate_bits = rate_bits; b.cap_height = cap_height;
+    b.coeffs = std::move(coeffs);
+    size_t n = b.n(), N = b.lde_n();
+    b.lde.alloc((size_t)ncols * N, s);
+    int c0 = 0;
+    for (size_t k = 0; k < col_ends.size(); k++) {
+        int c1 = col_ends[k];
+        ZKM_CHECK(c1 > c0, "bad column groups");
+        wait_group(k);
+        ntt_inverse(c.ntt, values + (size_t)c0 * n, n, b.coeffs.p + (size_t)c0 * n, n, c1 - c0, log_n, s);
+        lde_coset(c.ntt, b.coeffs.p + (size_t)c0 * n, n, b.lde.p + (size_t)c0 * N, N, c1 - c0, log_n, rate_bits, s);
+        c0 = c1;
+    }
+    merkle_alloc(b.tree, b.lde_bits(), cap_height, s);
+    lde_leaf_hash(b.lde.p, N, ncols, log_n, rate_bits, b.tree.digests.p, s);
+    merkle_build_from_leaf_digests(b.tree, s);
+}
+
 void batch_from_values_dev(Batch& b, DevBuf&& values, int ncols, int log_n, int rate_bits, int cap_height) {
     Ctx& c = ctx();
     ZKM_CHECK(ncols > 0, "empty polynomial batch");

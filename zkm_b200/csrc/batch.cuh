@@ -5,6 +5,8 @@
 #include "dev.cuh"
 #include "ntt.cuh"
 #include "merkle.cuh"
+#include <functional>
+#include <vector>
 
 namespace zkm {
 
@@ -32,5 +34,10 @@ struct Batch {
 // values (device, column-major ncols x n; consumed: may alias coeffs) -> batch
 void batch_from_values_dev(Batch& b, DevBuf&& values, int ncols, int log_n, int rate_bits, int cap_height);
 void batch_from_coeffs_dev(Batch& b, DevBuf&& coeffs, int ncols, int log_n, int rate_bits, int cap_height);
+// Same result as ifft + batch_from_coeffs_dev, but the columns are transformed group by group: group k = columns
+// [col_ends[k-1], col_ends[k]) is touched only after wait_group(k) returns (the uploader has delivered it), so the NTTs of the
+// first groups overlap the upload of the later ones; the leaf hashing (which needs every column) runs last.
+void batch_from_values_grouped_dev(Batch& b, const u64* values, DevBuf&& coeffs, int ncols, int log_n, int rate_bits, int cap_height,
+                                   const std::vector<int>& col_ends, const std::function<void(size_t)>& wait_group);
 
 }  // namespace zkm

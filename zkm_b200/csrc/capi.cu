@@ -182,15 +182,25 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
             for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
             in[t].values.alloc((size_t)tb->ncols * n, c.stream);
             ZKM_CUDA(cudaEventCreateWithFlags(&in[t].ready, cudaEventDisableTiming));
+            // tables above 256 MB arrive in 4 column groups so that their NTTs start before the whole table is resident
+            size_t bytes = (size_t)tb->ncols * n * sizeof(u64);
+            size_t group_threshold = (size_t)256 << 20;
+            if (const char* gt = std::getenv("ZKM_GROUP_BYTES")) group_threshold = (size_t)strtoull(gt, nullptr, 10);   // tests
+            if (bytes > group_threshold && tb->ncols >= 8) {
+                for (int g = 1; g <= 4; g++) in[t].group_ends.push_back((int)((size_t)tb->ncols * g / 4));
+                in[t].group_ready.resize(4, nullptr);
+                for (int g = 0; g < 4; g++) ZKM_CUDA(cudaEventCreateWithFlags(&in[t].group_ready[g], cudaEventDisableTiming));
+            }
         }
     }
     struct Uploader {
-        std::thread th; std::mutex mu; std::condition_variable cv; int recorded = 0; std::string error;
+        std::thread th; std::mutex mu; std::condition_variable cv; std::vector<char> done; std::vector<int> groups_done;
+        std::string error;
         ~Uploader() { if (th.joinable()) th.join(); }
     } up;
     struct EventGuard {
         std::vector<TableInput>& v; cudaStream_t cs; Uploader& u;
-        ~EventGuard() { if (u.th.joinable()) u.th.join(); cudaStreamSynchronize(cs); for (auto& x : v) if (x.ready) cudaEventDestroy(x.ready); }
+        ~EventGuard() { if (u.th.joinable()) u.th.join(); cudaStreamSynchronize(cs); for (auto& x : v) { if (x.ready) cudaEventDestroy(x.ready); for (cudaEvent_t e : x.group_ready) if (e) cudaEventDestroy(e); } }
     } guard{in, c.copy_stream, up};
     if (!d_tables) {
         int device = c.device;
@@ -199,24 +209,57 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
         for (uint32_t t = 0; t < num_tables; t++) dst[t] = in[t].values.p;
         std::vector<cudaEvent_t> evs(num_tables);
         for (uint32_t t = 0; t < num_tables; t++) evs[t] = in[t].ready;
-        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs] {
+        // smallest table first (the prover commits in the same order, prover.cu commit_order): the short commits run while the
+        // long uploads are still in flight, so the 2 GB CPU table never stalls the device (it did for ~15 ms in table order)
+        std::vector<size_t> bytes(num_tables);
+        for (uint32_t t = 0; t < num_tables; t++) bytes[t] = (size_t)tables[t].ncols << tables[t].log_n;
+        std::vector<size_t> order = commit_order(bytes);
+        up.done.assign(num_tables, 0);
+        up.groups_done.assign(num_tables, 0);
+        std::vector<std::vector<int>> gends(num_tables);
+        std::vector<std::vector<cudaEvent_t>> gevs(num_tables);
+        for (uint32_t t = 0; t < num_tables; t++) { gends[t] = in[t].group_ends; gevs[t] = in[t].group_ready; }
+        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs] {
             cudaSetDevice(device);
-            for (uint32_t t = 0; t < num_tables; t++) {
+            for (size_t t : order) {
                 size_t n = (size_t)1 << tables[t].log_n;
                 cudaError_t e = cudaSuccess;
-                for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++)
+                size_t g = 0;
+                // small tables (Keccak: 2431 columns of 512 bytes) would cost one driver call per column (~3 us each, 10 ms in
+                // total for the 8 small tables of a segment): gather them on the host and upload each with a single copy
+                if ((size_t)tables[t].ncols * n * sizeof(u64) <= ((size_t)8 << 20) && tables[t].ncols > 1) {
+                    std::vector<u64> pack((size_t)tables[t].ncols * n);
+                    for (uint32_t i = 0; i < tables[t].ncols; i++) memcpy(pack.data() + (size_t)i * n, tables[t].cols[i], n * sizeof(u64));
+                    e = cudaMemcpyAsync(dst[t], pack.data(), pack.size() * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);      // `pack` is released at the end of this scope
+                } else
+                for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++) {
                     e = cudaMemcpyAsync(dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                    if (e == cudaSuccess && g < gends[t].size() && (int)i + 1 == gends[t][g]) {
+                        e = cudaEventRecord(gevs[t][g], cs);
+                        g++;
+                        std::lock_guard<std::mutex> lk(up.mu);
+                        up.groups_done[t] = (int)g;
+                        up.cv.notify_all();
+                    }
+                }
                 if (e == cudaSuccess) e = cudaEventRecord(evs[t], cs);
-                std::lock_guard<std::mutex> g(up.mu);
+                std::lock_guard<std::mutex> lk2(up.mu);
                 if (e != cudaSuccess && up.error.empty()) up.error = cudaGetErrorString(e);
-                up.recorded = (int)t + 1;
+                up.done[t] = 1;
                 up.cv.notify_all();
             }
         });
         for (uint32_t t = 0; t < num_tables; t++)
+            in[t].wait_group = [&up, t](size_t k) {
+                std::unique_lock<std::mutex> lk(up.mu);
+                up.cv.wait(lk, [&] { return up.groups_done[t] > (int)k || up.done[t] != 0; });
+                if (!up.error.empty()) throw CudaError("trace upload failed: " + up.error);
+            };
+        for (uint32_t t = 0; t < num_tables; t++)
             in[t].wait_recorded = [&up, t] {
                 std::unique_lock<std::mutex> lk(up.mu);
-                up.cv.wait(lk, [&] { return up.recorded > (int)t; });
+                up.cv.wait(lk, [&] { return up.done[t] != 0; });
                 if (!up.error.empty()) throw CudaError("trace upload failed: " + up.error);
             };
     }

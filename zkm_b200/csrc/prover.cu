@@ -343,7 +343,12 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
     std::vector<TableJob> jobs(inputs.size());
     PhaseTimer pt0(s, "all");
     // trace commitments (prover.rs:144-167)
-    for (size_t t = 0; t < inputs.size(); t++) {
+    // The 12 commitments are independent (their caps enter the transcript afterwards, in table order), so they run smallest
+    // table first: with host inputs the uploader streams the tables in this same order (capi.cu) and the large tables arrive
+    // while the small ones are being committed.
+    std::vector<size_t> in_bytes(inputs.size());
+    for (size_t t = 0; t < inputs.size(); t++) in_bytes[t] = (size_t)inputs[t].ncols << inputs[t].log_n;
+    for (size_t t : commit_order(in_bytes)) {
         TableJob& j = jobs[t];
         j.kind = sys.kinds[t];
         j.layout = layout[t];
@@ -353,9 +358,18 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
         ZKM_CHECK(j.log_n + (int)cfg.rate_bits >= (int)cfg.cap_height && j.log_n >= 1, "trace too short");
         size_t n = (size_t)1 << j.log_n;
         j.values = std::move(inputs[t].values);
+        DevBuf coeffs((size_t)j.layout.ncols * n, s);
+        if (!inputs[t].group_ends.empty()) {
+            TableInput& in = inputs[t];
+            batch_from_values_grouped_dev(j.trace, j.values.p, std::move(coeffs), j.layout.ncols, j.log_n, cfg.rate_bits, cfg.cap_height,
+                                          in.group_ends, [&in, s](size_t k) {
+                                              in.wait_group(k);
+                                              ZKM_CUDA(cudaStreamWaitEvent(s, in.group_ready[k], 0));
+                                          });
+            continue;
+        }
         if (inputs[t].wait_recorded) inputs[t].wait_recorded();
         if (inputs[t].ready) ZKM_CUDA(cudaStreamWaitEvent(s, inputs[t].ready, 0));
-        DevBuf coeffs((size_t)j.layout.ncols * n, s);
         ntt_inverse(c.ntt, j.values.p, n, coeffs.p, n, j.layout.ncols, j.log_n, s);
         batch_from_coeffs_dev(j.trace, std::move(coeffs), j.layout.ncols, j.log_n, cfg.rate_bits, cfg.cap_height);
     }

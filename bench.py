@@ -124,6 +124,7 @@ class Segment:
         self.ra = (C.c_uint32 * 8)(*range(11, 19))
         self.userdata = bytes(32)
         self.last_proof_words = 0
+        self.kept = []
 
     def sync(self):
         err = C.c_void_p()
@@ -165,7 +166,7 @@ class Segment:
         self._keep = made
         self.tables = (self.zl.Table * 12)(*[m[0] for m in made])
 
-    def step_e2e(self):
+    def step_e2e(self, gather=True):
         """The reference-facing call: zkm_b200_prove_with_traces with HOST column pointers (H2D of every trace
         column inside, D2H of the finished proof buffer)."""
         lib = self.lib
@@ -173,7 +174,9 @@ class Segment:
         rc = lib.zkm_b200_prove_with_traces(self.tables, self.rb, self.ra, self.userdata, 32, C.byref(self.cfg), C.byref(out),
                                             C.byref(words), C.byref(err))
         proof = self._finish(rc, err, out, words, keep=self.world > 1)
-        if self.world > 1:
+        if self.world > 1 and not gather:
+            self.kept.append(proof)              # gathered by the caller once every worker has finished
+        elif self.world > 1:
             # the path's only exchange: finished proofs gathered on rank 0 (NCCL)
             from zkm_b200 import multi
             multi.gather_proofs([proof], [self.rank], self.world)
@@ -350,6 +353,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="U20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workers", type=int, default=2, help="proofs in flight per GPU (worker contexts)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -370,7 +374,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = zl.init(local)
-    seg = Segment(lib, args.workload, seed_offset=rank, rank=rank, world=world)
+    NW = max(1, args.workers)
+    # one synthetic segment per worker context: NW proofs are in flight on this GPU at any time (one host thread, one pair of
+    # streams and one arena each, include/zkm_b200.h "Worker contexts"); a step = NW segments, one per worker
+    segs = [Segment(lib, args.workload, seed_offset=rank * NW + i, rank=rank, world=world) for i in range(NW)]
+    seg = segs[0]
+    workers = [zl.Worker(lib) for _ in range(NW)]
 
     def barrier():
         if world > 1:
@@ -378,19 +387,63 @@ def main():
         torch.cuda.synchronize()
         seg.sync()
 
+    def timed_concurrent(step_name, warm, steps, after_join=None):
+        """Every worker thread runs `warm` untimed and then `steps` timed calls of Segment.<step_name>; the timed region is
+        bracketed by CUDA events on the (idle) main stream, recorded after a device-wide barrier and after every worker has
+        drained its stream."""
+        import threading
+        ready, go = threading.Barrier(NW + 1), threading.Barrier(NW + 1)
+        errors = []
+
+        def body(i):
+            try:
+                with workers[i]:
+                    for _ in range(warm):
+                        getattr(segs[i], step_name)()
+                    segs[i].sync()
+                    ready.wait(timeout=600)
+                    go.wait(timeout=600)
+                    for _ in range(steps):
+                        getattr(segs[i], step_name)()
+                    segs[i].sync()
+            except BaseException as e:           # never leave the other threads waiting on a barrier
+                errors.append(e)
+                ready.abort()
+                go.abort()
+        threads = [threading.Thread(target=body, args=(i,)) for i in range(NW)]
+        for t in threads:
+            t.start()
+        try:
+            ready.wait(timeout=600)
+            barrier()
+            err = C.c_void_p()
+            zl.check(lib, lib.zkm_b200_timer_start(C.byref(err)), err)
+            timed_concurrent.l0 = lib.zkm_b200_launch_count()
+            go.wait(timeout=600)
+        except threading.BrokenBarrierError:
+            pass
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        if after_join:
+            after_join()
+        ms, err = C.c_double(), C.c_void_p()
+        zl.check(lib, lib.zkm_b200_timer_stop(C.byref(ms), C.byref(err)), err)
+        timed_concurrent.launches = lib.zkm_b200_launch_count() - timed_concurrent.l0
+        return ms.value
+
     W = max(3, args.warmup)
-    for _ in range(W):
-        seg.step_device()
     # ---- device-resident timing: K steps with no instrumentation between launches ----
     lib.zkm_b200_profile_enable(0)
-    barrier()
-    l0 = lib.zkm_b200_launch_count()
     with ClockSampler(local) as clk:
-        t_dev = seg.timed(lambda: [seg.step_device() for _ in range(args.steps)])
+        t_dev = timed_concurrent("step_device", W, args.steps)
         barrier()
-    launches = lib.zkm_b200_launch_count() - l0
-    # ---- the same K steps again with a CUDA-event pair around every launch (per-family device times, roofline); the events
+    launches = timed_concurrent.launches
+    # ---- K single-context steps with a CUDA-event pair around every launch (per-family device times, roofline); the events
     # serialise the launch-bound phases of the 8 small tables, so this pass is reported next to the clean one, not instead ----
+    for _ in range(2):
+        seg.step_device()
     lib.zkm_b200_profile_enable(1)
     seg.profile_reset()
     barrier()
@@ -399,11 +452,22 @@ def main():
     fam = seg.profile_families()
     lib.zkm_b200_profile_enable(0)
     # ---- end to end through the C ABI with host buffers ----
-    seg.prepare_host()
-    seg.step_e2e()
+    for sg in segs:
+        sg.prepare_host()
+
+    def gather_all():
+        if world > 1:                            # the path's only exchange: finished proofs gathered on rank 0 (NCCL)
+            from zkm_b200 import multi
+            proofs = [p for sg in segs for p in sg.kept]
+            multi.gather_proofs(proofs, [rank * len(proofs) + k for k in range(len(proofs))], len(proofs) * world)
+            for sg in segs:
+                sg.kept = []
+    for sg in segs:
+        sg.step_e2e_nogather = lambda sg=sg: sg.step_e2e(gather=False)
+    t_e2e = timed_concurrent("step_e2e_nogather", 1, args.steps, after_join=gather_all)
     barrier()
-    t_e2e = seg.timed(lambda: [seg.step_e2e() for _ in range(args.steps)])
-    barrier()
+    for w in workers:
+        w.close()
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -416,17 +480,19 @@ def main():
         # dominant family (Poseidon leaf hashing, integer-ALU bound) is named next to it with every family's share
         ntt = fam.get("ntt_pass", top[1])
         ach = ntt["bytes"] / (ntt["ms"] * 1e-3) / 1e9 if ntt["ms"] else 0.0
-        value = args.steps * world / (t_dev * 1e-3)
-        e2e = args.steps * world / (t_e2e * 1e-3)
+        value = args.steps * NW * world / (t_dev * 1e-3)
+        e2e = args.steps * NW * world / (t_e2e * 1e-3)
         line = {"metric": seg.metric, "value": value, "unit": seg.unit, "n_gpus": world, "steps": args.steps, "warmup": W,
                 "ms_per_step": t_dev / args.steps, "ms_per_step_instrumented": t_prof / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 (Goldilocks)", "data": "synthetic",
                 "config": {"workload": args.workload, "stages": seg.stages, "log_heights": seg.heights,
                            "l2": f"inputs {seg.input_bytes / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)",
-                           "parallelism": f"{world} independent segments (one per GPU)"},
+                           "segments_per_step": NW,
+                           "parallelism": f"{world} GPU(s) x {NW} worker contexts, one independent segment each (a step = "
+                                          f"{NW * world} proofs)"},
                 "e2e": {"value": e2e, "unit": seg.unit, "ms_per_step": t_e2e / args.steps,
-                        "h2d_bytes_per_step": seg.input_bytes, "d2h_bytes_per_step": seg.output_bytes},
+                        "h2d_bytes_per_step": seg.input_bytes * NW, "d2h_bytes_per_step": seg.output_bytes * NW},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "peak_kind": peak_kind, "traffic": seg.ncu_traffic("ntt_pass"),

@@ -59,6 +59,16 @@ uint64_t zkm_b200_launch_count(void);
 /* Blocks until all device work queued by the library has finished. */
 int zkm_b200_sync(char** err);
 
+/* Worker contexts.  The library is not re-entrant on one context (reference callers are single-threaded at this level:
+ * `&mut TimingTree`, prover.rs:130-140), but a host thread may bind a worker context -- its own streams, twiddle tables and
+ * device-memory arena on the initialised device -- and every call it makes then runs there.  Two threads bound to two
+ * workers can prove two segments at once: the latency-bound phases of one proof (small tables, transcript round trips)
+ * overlap the throughput-bound kernels of the other.  Proofs do not depend on the context they were computed on. */
+typedef struct zkm_worker zkm_worker_t;
+int zkm_b200_worker_create(zkm_worker_t** out, char** err);
+int zkm_b200_worker_bind(zkm_worker_t* w, char** err);      /* NULL: back to the process-wide context */
+void zkm_b200_worker_destroy(zkm_worker_t* w);
+
 /* CUDA-event stopwatch on the library's stream (bench.py times the whole step with it). */
 int zkm_b200_timer_start(char** err);
 int zkm_b200_timer_stop(double* ms, char** err);

@@ -169,3 +169,35 @@ def test_grouped_upload_commit_is_identical(zkm, orc, monkeypatch):
     grouped = zl.prove_system(zkm, tr.SYSTEM_KECCAK, traces)
     assert _first_diff(ref, grouped) is None
     assert _first_diff(grouped, binding.prove_system(orc, tr.SYSTEM_KECCAK, traces)) is None
+
+
+def test_two_worker_contexts_prove_concurrently(zkm, orc):
+    """Two host threads, each bound to its own worker context (include/zkm_b200.h), prove different Systems at the same time;
+    every proof equals the one computed alone on the process-wide context."""
+    import threading
+    jobs = [(tr.SYSTEM_KECCAK, tr.keccak_system_traces()), (tr.SYSTEM_CPU, tr.cpu_system_traces())]
+    alone = [zl.prove_system(zkm, sid, t) for sid, t in jobs]
+    workers = [zl.Worker(zkm) for _ in jobs]
+    out, errors = [[], []], []
+
+    def body(i):
+        try:
+            with workers[i]:
+                for _ in range(3):
+                    out[i].append(zl.prove_system(zkm, jobs[i][0], jobs[i][1]))
+        except BaseException as e:
+            errors.append(e)
+    threads = [threading.Thread(target=body, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for w in workers:
+        w.close()
+    assert not errors, errors
+    for i in range(2):
+        assert len(out[i]) == 3
+        for p in out[i]:
+            assert _first_diff(p, alone[i]) is None
+    # and the process-wide context still works after the workers are gone
+    assert _first_diff(zl.prove_system(zkm, jobs[0][0], jobs[0][1]), alone[0]) is None

@@ -5,57 +5,67 @@
 namespace zkm {
 
 static std::unique_ptr<Ctx> g_ctx;
+// A host thread may bind a worker context (zkm_b200_worker_bind): its own streams, NTT tables and arena, so that two proofs
+// can be in flight on one device (the latency-bound phases of one overlap the throughput-bound kernels of the other).
+static thread_local Ctx* t_ctx = nullptr;
 
-// ---- arena (dev.cuh)
+// ---- arena (dev.cuh): one per context, because a freed block is handed to the next user on the SAME stream only
+struct Arena {
+    std::multimap<size_t, void*> free_blocks;       // size -> block
+    size_t cached = 0, live = 0;
+};
 namespace {
 // heap-allocated and never destroyed: DevBufs owned by other statics may be released during process exit
-std::multimap<size_t, void*>& g_free_blocks = *new std::multimap<size_t, void*>();       // size -> block
-size_t g_cached = 0, g_live = 0;
+Arena& g_arena0 = *new Arena();
 const size_t ARENA_CACHE_LIMIT = (size_t)150 << 30;
+Arena& cur_arena() { return (t_ctx && t_ctx->arena) ? *t_ctx->arena : g_arena0; }
+void arena_trim_one(Arena& a) {
+    cudaDeviceSynchronize();
+    for (auto& kv : a.free_blocks) cudaFree(kv.second);
+    a.free_blocks.clear();
+    a.cached = 0;
+}
 }
 void* arena_alloc(size_t bytes) {
+    Arena& A = cur_arena();
     bytes = (bytes + 511) & ~(size_t)511;
-    auto it = g_free_blocks.lower_bound(bytes);
+    auto it = A.free_blocks.lower_bound(bytes);
     // reuse a cached block when it is not wastefully larger than the request
-    if (it != g_free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
+    if (it != A.free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
         void* p = it->second;
-        g_cached -= it->first;
-        g_live += it->first;
-        g_free_blocks.erase(it);
+        A.cached -= it->first;
+        A.live += it->first;
+        A.free_blocks.erase(it);
         return p;
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        arena_trim();                              // give cached blocks back and retry once
+        arena_trim_one(A);                         // give cached blocks back and retry once
         e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
-    g_live += bytes;
+    A.live += bytes;
     return p;
 }
 void arena_free(void* p, size_t bytes) {
     if (!p) return;
+    Arena& A = cur_arena();
     bytes = (bytes + 511) & ~(size_t)511;
-    // find the true block size: blocks handed out from the cache may be larger than the request; the size
-    // recorded here is the request rounded up, which is what lower_bound matched against, so re-insert
-    // under that size (never larger than the real block)
-    g_live -= bytes <= g_live ? bytes : g_live;
-    if (g_cached + bytes > ARENA_CACHE_LIMIT) arena_trim();
-    g_free_blocks.emplace(bytes, p);
-    g_cached += bytes;
+    // blocks handed out from the cache may be larger than the request; the size recorded here is the request rounded up,
+    // which is what lower_bound matched against, so re-insert under that size (never larger than the real block)
+    A.live -= bytes <= A.live ? bytes : A.live;
+    if (A.cached + bytes > ARENA_CACHE_LIMIT) arena_trim_one(A);
+    A.free_blocks.emplace(bytes, p);
+    A.cached += bytes;
 }
-void arena_trim() {
-    cudaDeviceSynchronize();
-    for (auto& kv : g_free_blocks) cudaFree(kv.second);
-    g_free_blocks.clear();
-    g_cached = 0;
-}
-size_t arena_cached_bytes() { return g_cached; }
+void arena_trim() { arena_trim_one(cur_arena()); }
+size_t arena_cached_bytes() { return cur_arena().cached; }
 
 bool ctx_ready() { return (bool)g_ctx; }
 Ctx& ctx() {
+    if (t_ctx) return *t_ctx;
     if (!g_ctx) throw std::runtime_error("zkm_b200: not initialised (call zkm_b200_init; a CUDA device is required)");
     return *g_ctx;
 }
@@ -76,6 +86,35 @@ void ctx_init(int device) {
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     g_ctx = std::move(c);
+}
+Ctx* worker_create() {
+    ZKM_CHECK(g_ctx, "zkm_b200: not initialised");
+    ZKM_CUDA(cudaSetDevice(g_ctx->device));
+    auto c = std::make_unique<Ctx>();
+    c->device = g_ctx->device;
+    c->arena = new Arena();
+    ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    return c.release();
+}
+void worker_bind(Ctx* w) {
+    if (w) ZKM_CUDA(cudaSetDevice(w->device));
+    t_ctx = w;
+}
+void worker_destroy(Ctx* w) {
+    if (!w) return;
+    Ctx* prev = t_ctx;
+    t_ctx = w;                                     // the worker's tables go back to the worker's arena
+    cudaStreamSynchronize(w->stream);
+    cudaStreamSynchronize(w->copy_stream);
+    cudaStream_t s0 = w->stream, s1 = w->copy_stream;
+    Arena* a = w->arena;
+    delete w;                                      // ~NttTables releases its buffers while t_ctx still names this context
+    t_ctx = (prev == w) ? nullptr : prev;
+    arena_trim_one(*a);
+    delete a;
+    cudaStreamDestroy(s0);
+    cudaStreamDestroy(s1);
 }
 void ctx_shutdown() {
     if (!g_ctx) return;

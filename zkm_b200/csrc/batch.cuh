@@ -10,8 +10,10 @@
 
 namespace zkm {
 
+struct Arena;
 struct Ctx {
     int device = -1;
+    Arena* arena = nullptr;                // worker contexts own one; the process-wide context uses the default arena
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = 0;          // host->device trace uploads, overlapped with the commitments
     NttTables ntt;
@@ -20,6 +22,11 @@ Ctx& ctx();                    // throws if zkm_b200_init has not succeeded
 bool ctx_ready();
 void ctx_init(int device);
 void ctx_shutdown();
+// Worker contexts: a second (third, ...) set of streams + tables + arena on the initialised device.  A host thread that has
+// bound one runs every library call on it; two bound threads can prove concurrently.
+Ctx* worker_create();
+void worker_bind(Ctx* w);       // nullptr unbinds
+void worker_destroy(Ctx* w);
 
 struct Batch {
     int ncols = 0, log_n = 0, rate_bits = 0, cap_height = 0;

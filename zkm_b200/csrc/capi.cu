@@ -59,6 +59,21 @@ int zkm_b200_sync(char** err) {
     ZKM_API_END
 }
 
+int zkm_b200_worker_create(zkm_worker_t** out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(out, "null argument");
+    *out = (zkm_worker_t*)worker_create();
+    ZKM_API_END
+}
+int zkm_b200_worker_bind(zkm_worker_t* w, char** err) {
+    ZKM_API_BEGIN
+    worker_bind((Ctx*)w);
+    ZKM_API_END
+}
+void zkm_b200_worker_destroy(zkm_worker_t* w) {
+    try { worker_destroy((Ctx*)w); } catch (...) {}
+}
+
 static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 int zkm_b200_timer_start(char** err) {
     ZKM_API_BEGIN

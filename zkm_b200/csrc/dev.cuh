@@ -26,7 +26,7 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 
 // Count of kernel launches issued by this library (bench.py reports it as gpu_launches).
 extern unsigned long long g_launch_count;
-#define ZKM_LAUNCHED() do { ++::zkm::g_launch_count; ZKM_CUDA(cudaGetLastError()); } while (0)
+#define ZKM_LAUNCHED() do { __atomic_fetch_add(&::zkm::g_launch_count, 1ULL, __ATOMIC_RELAXED); ZKM_CUDA(cudaGetLastError()); } while (0)
 
 // Device memory arena: blocks come from cudaMalloc once and are then recycled through a size-keyed free
 // list, so a steady-state proof issues no driver allocation calls at all (the stream-ordered driver pool

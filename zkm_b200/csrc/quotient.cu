@@ -13,6 +13,8 @@
 #include "aux.cuh"
 #include "tables/registry.h"
 
+#include <mutex>
+
 namespace zkm {
 
 struct LdeRow {
@@ -282,6 +284,11 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
     // cooperative variant while the 2n points cannot fill the machine: 32 points x 16 workers per CTA
     const bool coop = 2 * n <= 8192;
+    // c_quotient_alpha is one constant-memory slot per device: with several worker contexts the upload + kernel of one proof
+    // must not interleave with another's (the launch below is followed by a stream synchronisation, so holding the lock until
+    // the end of this function is enough)
+    static std::mutex quotient_mu;
+    std::lock_guard<std::mutex> quotient_lock(quotient_mu);
     quotient_kernel_t k = quotient_kernel_for(kind, coop, ha, s);
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
     if (coop) {

@@ -31,6 +31,7 @@ EXPORTS = [
     "zkm_b200_launch_count", "zkm_b200_sync", "zkm_b200_commit_values", "zkm_b200_commit_coeffs",
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
+    "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
@@ -73,6 +74,10 @@ def load():
                                                  C.c_uint32, C.POINTER(StarkConfig), C.POINTER(u64p), C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_void_p)]
     lib.zkm_b200_free.argtypes = [C.c_void_p]
+    lib.zkm_b200_worker_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_worker_bind.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_worker_destroy.argtypes = [C.c_void_p]
+    lib.zkm_b200_worker_destroy.restype = None
     lib.zkm_b200_synth_trace_device.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.zkm_b200_synth_trace.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, u64p, C.POINTER(C.c_void_p)]
     lib.zkm_b200_system_shape.argtypes = [C.c_int, u32p, u32p, C.c_uint32, C.POINTER(C.c_void_p)]
@@ -152,6 +157,31 @@ def prove_system(lib, system_id, traces, roots_before=None, roots_after=None, us
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)
     return proof
+
+
+class Worker:
+    """A worker context bound to the calling thread for the duration of a `with` block (include/zkm_b200.h)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.h = C.c_void_p()
+        err = C.c_void_p()
+        check(lib, lib.zkm_b200_worker_create(C.byref(self.h), C.byref(err)), err)
+
+    def __enter__(self):
+        err = C.c_void_p()
+        check(self.lib, self.lib.zkm_b200_worker_bind(self.h, C.byref(err)), err)
+        return self
+
+    def __exit__(self, *exc):
+        err = C.c_void_p()
+        self.lib.zkm_b200_worker_bind(None, C.byref(err))
+        return False
+
+    def close(self):
+        if self.h:
+            self.lib.zkm_b200_worker_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 def prove_with_traces(lib, traces, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):

@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="U20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workers", type=int, default=2, help="proofs in flight per GPU (worker contexts)")
+    ap.add_argument("--workers", type=int, default=0, help="proofs in flight per GPU (worker contexts); 0 = 3, fewer on small hosts")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -374,7 +374,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = zl.init(local)
-    NW = max(1, args.workers)
+    # measured on one B200 (profiles/r1c_workers_sweep.txt): 1 worker 2.88, 2: 2.99, 3: 3.16, 4: 3.20 proofs/s
+    NW = args.workers if args.workers > 0 else max(1, min(3, (os.cpu_count() or 2) // (2 * max(1, world))))
     # one synthetic segment per worker context: NW proofs are in flight on this GPU at any time (one host thread, one pair of
     # streams and one arena each, include/zkm_b200.h "Worker contexts"); a step = NW segments, one per worker
     segs = [Segment(lib, args.workload, seed_offset=rank * NW + i, rank=rank, world=world) for i in range(NW)]

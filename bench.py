@@ -372,6 +372,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = zl.init(local)
     # measured on one B200 (profiles/r1c_workers_sweep.txt): 1 worker 2.88, 2: 2.99, 3: 3.16, 4: 3.20 proofs/s

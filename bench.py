@@ -345,6 +345,28 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run this rank's host threads, and first-touch its pinned trace buffers, on the CPU socket the GPU
+    hangs off (sysfs local_cpulist of the GPU's PCI function).  Best effort: returns the CPU list used, or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                       # sysfs uses a 4-digit PCI domain
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return f"{min(cpus)}-{max(cpus)} ({len(cpus)} cpus)"
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,6 +392,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # keep stdout to the one JSON line
@@ -490,7 +513,7 @@ def main():
                 "dtype": "u64 (Goldilocks)", "data": "synthetic",
                 "config": {"workload": args.workload, "stages": seg.stages, "log_heights": seg.heights,
                            "l2": f"inputs {seg.input_bytes / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)",
-                           "segments_per_step": NW,
+                           "segments_per_step": NW, "numa_binding": numa,
                            "parallelism": f"{world} GPU(s) x {NW} worker contexts, one independent segment each (a step = "
                                           f"{NW * world} proofs)"},
                 "e2e": {"value": e2e, "unit": seg.unit, "ms_per_step": t_e2e / args.steps,

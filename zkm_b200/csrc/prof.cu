@@ -12,6 +12,7 @@ namespace {
 struct Pending { std::string name; cudaEvent_t e0, e1; double bytes; };
 struct Total { double ms = 0; unsigned long long launches = 0; double bytes = 0; };
 bool g_on = false;
+std::mutex g_mu;                               // worker contexts may profile from several host threads
 std::vector<Pending> g_pending;
 std::vector<cudaEvent_t> g_pool;
 std::map<std::string, Total> g_totals;
@@ -39,18 +40,21 @@ void resolve() {
 
 ProfScope::ProfScope(const char* name_, cudaStream_t s_, double b) : name(name_), s(s_), bytes(b) {
     if (!g_on) return;
+    std::lock_guard<std::mutex> lk(g_mu);
     e0 = get_event(); e1 = get_event();
     cudaEventRecord(e0, s);
 }
 ProfScope::~ProfScope() {
     if (!e0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
     cudaEventRecord(e1, s);
     g_pending.push_back({name, e0, e1, bytes});
     if (g_pending.size() > 8192) resolve();
 }
 void prof_enable(bool on) { g_on = on; }
-void prof_reset() { resolve(); g_totals.clear(); g_order.clear(); }
+void prof_reset() { std::lock_guard<std::mutex> lk(g_mu); resolve(); g_totals.clear(); g_order.clear(); }
 bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
     resolve();
     auto it = g_totals.find(name);
     if (it == g_totals.end()) return false;
@@ -60,6 +64,7 @@ bool prof_get(const char* name, double* ms, unsigned long long* launches, double
     return true;
 }
 std::string prof_names() {
+    std::lock_guard<std::mutex> lk(g_mu);
     resolve();
     std::string r;
     for (auto& n : g_order) { if (!r.empty()) r += "\n"; r += n; }

@@ -4,8 +4,10 @@ the reference's witness generation produces (test infrastructure).  Restated fro
 every instruction used here, cited at each method), witness/util.rs:48-349 (register/memory channel helpers),
 generation/mod.rs:169-186 (exit padding rows), cpu/bootstrap_kernel.rs (memory image written through the GP channels by
 bootstrap rows; simplified to plain image writes, the constraints :308-351 ask no more), memory/memory_stark.rs:44-244
-(sorting, fill_gaps, padding, first-change flags, range check, counter, frequencies).
-Syscalls and the hash precompiles are not interpreted."""
+(sorting, fill_gaps, padding, first-change flags, range check, counter, frequencies); syscalls (operation.rs:1460-1684:
+brk, mmap, clone, exit_group, read, write, fcntl, set_thread_area, unknown numbers) and the Keccak / SHA-extend / SHA-compress
+precompile rows (operation.rs:1101-1458, witness/util.rs:370-694), image-id rows of the bootstrap (bootstrap_kernel.rs:70-163).
+Not interpreted: the hint / verify / commit / preimage syscalls (host-side input streams) and the page-hash rows."""
 import numpy as np
 
 import arith_gen as ag

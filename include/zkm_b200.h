@@ -110,6 +110,20 @@ char* zkm_b200_profile_families(void);
 int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t roots_before[8], const uint32_t roots_after[8],
                                const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
                                uint64_t** proof_out, size_t* proof_words, char** err);
+/* A table as its generator leaves it: 2^log_n rows of ncols words, row-major -- the `Vec<[F; COLUMNS]>` that
+ * trace_rows_to_poly_values (reference util.rs:37-47) transposes on the CPU in Traces::into_tables
+ * (witness/traces.rs:274-305).  Passing the rows moves that transposition onto the device. */
+typedef struct {
+    const uint64_t* rows;
+    uint32_t ncols;
+    uint32_t log_n;
+} zkm_table_rows_t;
+/* prove_with_traces where table t is taken from row_tables[t] when row_tables[t].rows != NULL and from tables[t]
+ * otherwise (Arithmetic and Memory are built column-wise upstream; the other ten tables come as rows). */
+int zkm_b200_prove_with_trace_rows(const zkm_table_t tables[12], const zkm_table_rows_t row_tables[12],
+                                   const uint32_t roots_before[8], const uint32_t roots_after[8], const uint8_t* userdata,
+                                   uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out,
+                                   size_t* proof_words, char** err);
 /* Same prover over another System of tables (zkm_b200/csrc/tables/systems.h: 0 = AllStark, 1 = Logic,
  * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory): small Systems whose valid traces can be
  * generated without the MIPS emulator, for prove -> verify parity tests. */

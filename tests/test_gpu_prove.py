@@ -201,3 +201,16 @@ def test_two_worker_contexts_prove_concurrently(zkm, orc):
             assert _first_diff(p, alone[i]) is None
     # and the process-wide context still works after the workers are gone
     assert _first_diff(zl.prove_system(zkm, jobs[0][0], jobs[0][1]), alone[0]) is None
+
+
+def test_row_major_tables_give_the_same_proof(zkm, orc):
+    """zkm_b200_prove_with_trace_rows: the ten tables the reference generates row by row (everything but Arithmetic and Memory,
+    witness/traces.rs:274-305) are handed over as rows and transposed on the device (reference util.rs:37-47 does it on
+    the CPU); the proof must be the one the column-major call returns."""
+    traces = tr.all_stark_valid_traces(orc, sha_blocks=12)
+    ref = zl.prove_with_traces(zkm, traces)
+    as_rows = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10}
+    mixed = [np.ascontiguousarray(t.T) if k in as_rows else t for k, t in enumerate(traces)]
+    got = zl.prove_with_trace_rows(zkm, mixed, as_rows)
+    assert _first_diff(ref, got) is None
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, got) is None

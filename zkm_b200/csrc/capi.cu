@@ -169,11 +169,18 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
     ZKM_API_END
 }
 
-static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_tables, const uint64_t* const* d_tables,
+static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t num_tables, const uint64_t* const* d_tables,
                         const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
-                        const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words) {
+                        const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
+                        const zkm_table_rows_t* row_tables = nullptr) {
     Ctx& c = ctx();
-    ZKM_CHECK(tables && roots_before && roots_after && cfg && proof_out && proof_words, "null argument");
+    ZKM_CHECK(tables_in && roots_before && roots_after && cfg && proof_out && proof_words, "null argument");
+    // tables given as rows (zkm_b200_prove_with_trace_rows): shape from the row descriptor, data uploaded as one block
+    std::vector<zkm_table_t> merged(tables_in, tables_in + num_tables);
+    for (uint32_t t = 0; t < num_tables && row_tables; t++)
+        if (row_tables[t].rows) { merged[t].cols = nullptr; merged[t].ncols = row_tables[t].ncols; merged[t].log_n = row_tables[t].log_n; }
+    const zkm_table_t* tables = merged.data();
+    std::vector<DevBuf> row_staging(num_tables);
     ZKM_CHECK(userdata || userdata_len == 0, "null userdata");
     StarkCfg sc;
     sc.rate_bits = cfg->rate_bits; sc.cap_height = cfg->cap_height; sc.pow_bits = cfg->pow_bits; sc.num_queries = cfg->num_queries;
@@ -193,10 +200,16 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
             // pageable and, on this platform, also for pinned sources), so table t+1.. stream in while table t is
             // being committed; the prover waits on `ready` before touching a buffer
             const zkm_table_t* tb = &tables[t];
-            ZKM_CHECK(tb->cols && tb->ncols > 0, "null/empty table");
-            for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
+            const bool as_rows = row_tables && row_tables[t].rows;
+            ZKM_CHECK((tb->cols || as_rows) && tb->ncols > 0, "null/empty table");
+            if (!as_rows) for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
             in[t].values.alloc((size_t)tb->ncols * n, c.stream);
             ZKM_CUDA(cudaEventCreateWithFlags(&in[t].ready, cudaEventDisableTiming));
+            if (as_rows) {
+                ZKM_CHECK(tb->log_n >= 5, "row-major tables need at least 32 rows");
+                row_staging[t].alloc((size_t)tb->ncols * n, c.stream);
+                continue;                       // one block: no column groups
+            }
             // tables above 256 MB arrive in 4 column groups so that their NTTs start before the whole table is resident
             size_t bytes = (size_t)tb->ncols * n * sizeof(u64);
             size_t group_threshold = (size_t)256 << 20;
@@ -234,12 +247,30 @@ static int prove_common(int system_id, const zkm_table_t* tables, uint32_t num_t
         std::vector<std::vector<int>> gends(num_tables);
         std::vector<std::vector<cudaEvent_t>> gevs(num_tables);
         for (uint32_t t = 0; t < num_tables; t++) { gends[t] = in[t].group_ends; gevs[t] = in[t].group_ready; }
-        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs] {
+        std::vector<const u64*> rows_src(num_tables, nullptr);
+        std::vector<u64*> rows_stage(num_tables, nullptr);
+        for (uint32_t t = 0; t < num_tables; t++)
+            if (row_tables && row_tables[t].rows) { rows_src[t] = row_tables[t].rows; rows_stage[t] = row_staging[t].p; }
+        // the staging buffers and `values` were allocated on the compute stream: the copy stream must not run ahead of that
+        cudaEvent_t alloc_done;
+        ZKM_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+        ZKM_CUDA(cudaEventRecord(alloc_done, c.stream));
+        ZKM_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
+        ZKM_CUDA(cudaEventDestroy(alloc_done));
+        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage] {
             cudaSetDevice(device);
             for (size_t t : order) {
                 size_t n = (size_t)1 << tables[t].log_n;
                 cudaError_t e = cudaSuccess;
                 size_t g = 0;
+                if (rows_src[t]) {
+                    // rows as generated (one contiguous block), transposed into column-major on the device
+                    e = cudaMemcpyAsync(rows_stage[t], rows_src[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                    if (e == cudaSuccess) {
+                        try { transpose_rows_to_cols(rows_stage[t], dst[t], n, (int)tables[t].ncols, cs); }
+                        catch (const std::exception&) { e = cudaErrorLaunchFailure; }
+                    }
+                } else
                 // small tables (Keccak: 2431 columns of 512 bytes) would cost one driver call per column (~3 us each, 10 ms in
                 // total for the 8 small tables of a segment): gather them on the host and upload each with a single copy
                 if ((size_t)tables[t].ncols * n * sizeof(u64) <= ((size_t)8 << 20) && tables[t].ncols > 1) {
@@ -320,6 +351,16 @@ int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t root
     prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
     ZKM_API_END
 }
+int zkm_b200_prove_with_trace_rows(const zkm_table_t* tables, const zkm_table_rows_t* row_tables, const uint32_t* roots_before,
+                                   const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                                   const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(row_tables, "null argument");
+    prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words,
+                 row_tables);
+    ZKM_API_END
+}
+
 
 void zkm_b200_batch_free(zkm_batch_t* b) {
     if (!b) return;

@@ -84,6 +84,9 @@ bool prof_get(const char* name, double* ms, unsigned long long* launches, double
 // Names seen so far, '\n'-separated.
 std::string prof_names();
 
+// Row-major n x ncols block -> column-major ncols x n (transpose.cu).
+void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cudaStream_t s);
+
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 struct PowTable {
     const u64* lo = nullptr;

@@ -32,7 +32,7 @@ EXPORTS = [
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 
@@ -197,6 +197,42 @@ def prove_with_traces(lib, traces, roots_before=None, roots_after=None, userdata
     words = C.c_size_t()
     err = C.c_void_p()
     rc = lib.zkm_b200_prove_with_traces(arr, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words), C.byref(err))
+    check(lib, rc, err)
+    proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+    lib.zkm_b200_free(out)
+    return proof
+
+
+class TableRows(C.Structure):
+    _fields_ = [("rows", C.POINTER(C.c_uint64)), ("ncols", C.c_uint32), ("log_n", C.c_uint32)]
+
+
+def prove_with_trace_rows(lib, traces, as_rows, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):
+    """zkm_b200_prove_with_trace_rows: traces[t] is (ncols, n) column-major, except for t in `as_rows`, which is passed as the
+    (n, ncols) row-major block its generator produced."""
+    cfg = cfg or standard_fast_config(lib)
+    keep, cols, rows = [], [], []
+    for t, a in enumerate(traces):
+        if t in as_rows:
+            r = np.ascontiguousarray(a, dtype=np.uint64)
+            assert r.ndim == 2
+            keep.append(r)
+            cols.append(Table(None, r.shape[1], r.shape[0].bit_length() - 1))
+            rows.append(TableRows(r.ctypes.data_as(C.POINTER(C.c_uint64)), r.shape[1], r.shape[0].bit_length() - 1))
+        else:
+            m = make_table(np.ascontiguousarray(a))
+            keep.append(m)
+            cols.append(m[0])
+            rows.append(TableRows(None, 0, 0))
+    carr, rarr = (Table * 12)(*cols), (TableRows * 12)(*rows)
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+    lib.zkm_b200_prove_with_trace_rows.argtypes = [C.POINTER(Table), C.POINTER(TableRows), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                                   C.c_char_p, C.c_uint32, C.POINTER(StarkConfig), C.POINTER(C.POINTER(C.c_uint64)),
+                                                   C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    rc = lib.zkm_b200_prove_with_trace_rows(carr, rarr, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words),
+                                            C.byref(err))
     check(lib, rc, err)
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)

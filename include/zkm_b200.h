@@ -125,8 +125,10 @@ int zkm_b200_prove_with_trace_rows(const zkm_table_t tables[12], const zkm_table
                                    uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out,
                                    size_t* proof_words, char** err);
 /* Same prover over another System of tables (zkm_b200/csrc/tables/systems.h: 0 = AllStark, 1 = Logic,
- * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory): small Systems whose valid traces can be
- * generated without the MIPS emulator, for prove -> verify parity tests. */
+ * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory, 5 = Arithmetic, 6 = Keccak+KeccakSponge+Logic+Memory,
+ * 7 = Poseidon+PoseidonSponge+Memory, 8 = ShaExtend+ShaExtendSponge+Logic+Memory, 9 = ShaCompress+ShaCompressSponge+
+ * Logic+Memory, 10 = Cpu+Arithmetic+Logic+Memory): slices of AllStark with its real cross-table lookups, whose valid
+ * traces the tests generate from restated witness generators, for prove -> verify parity tests. */
 int zkm_b200_prove_system(int system_id, const zkm_table_t* tables, uint32_t num_tables, const uint32_t* roots_before,
                           const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
                           const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err);

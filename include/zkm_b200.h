@@ -119,7 +119,10 @@ typedef struct {
     uint32_t log_n;
 } zkm_table_rows_t;
 /* prove_with_traces where table t is taken from row_tables[t] when row_tables[t].rows != NULL and from tables[t]
- * otherwise (Arithmetic and Memory are built column-wise upstream; the other ten tables come as rows). */
+ * otherwise.  Ten tables come out of their generators as finished rows.  The Arithmetic table (index 0) passed as rows is
+ * taken as ArithmeticStark::generate_trace has it BEFORE generate_range_checks (arithmetic_stark.rs:155-192: operation rows
+ * + zero padding to >= 2^16 rows): RANGE_COUNTER and RC_FREQUENCIES are then generated on the device (:127-153), and a
+ * shared cell >= 2^16 is reported as the reference's assertion text.  Memory is sorted column-wise upstream: pass columns. */
 int zkm_b200_prove_with_trace_rows(const zkm_table_t tables[12], const zkm_table_rows_t row_tables[12],
                                    const uint32_t roots_before[8], const uint32_t roots_after[8], const uint8_t* userdata,
                                    uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out,

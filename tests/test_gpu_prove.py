@@ -214,3 +214,20 @@ def test_row_major_tables_give_the_same_proof(zkm, orc):
     got = zl.prove_with_trace_rows(zkm, mixed, as_rows)
     assert _first_diff(ref, got) is None
     assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, got) is None
+
+
+def test_arithmetic_rows_get_their_range_checks_on_the_device(zkm, orc):
+    """Arithmetic rows as ArithmeticStark::generate_trace has them before generate_range_checks (arithmetic_stark.rs:155-192):
+    the counter and frequency columns come from the device (reference :127-153) and the proof equals the column-major one."""
+    import arith_gen as ag
+    traces = tr.all_stark_valid_traces(orc)
+    ref = zl.prove_with_traces(zkm, traces)
+    rows = np.ascontiguousarray(traces[0].T).copy()
+    rows[:, ag.RANGE_COUNTER] = 0
+    rows[:, ag.RC_FREQUENCIES] = 0
+    mixed = [rows] + traces[1:]
+    got = zl.prove_with_trace_rows(zkm, mixed, {0})
+    assert _first_diff(ref, got) is None
+    rows[5, ag.IN2] = 1 << 16                  # not range-checkable
+    with pytest.raises(zl.ZkmError, match="exceeds the max range value"):
+        zl.prove_with_trace_rows(zkm, [rows] + traces[1:], {0})

@@ -181,6 +181,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
         if (row_tables[t].rows) { merged[t].cols = nullptr; merged[t].ncols = row_tables[t].ncols; merged[t].log_n = row_tables[t].log_n; }
     const zkm_table_t* tables = merged.data();
     std::vector<DevBuf> row_staging(num_tables);
+    DevBuf bad_flag(1, c.stream);              // raised by the device-side Arithmetic range check (rows path)
     ZKM_CHECK(userdata || userdata_len == 0, "null userdata");
     StarkCfg sc;
     sc.rate_bits = cfg->rate_bits; sc.cap_height = cfg->cap_height; sc.pow_bits = cfg->pow_bits; sc.num_queries = cfg->num_queries;
@@ -257,7 +258,11 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
         ZKM_CUDA(cudaEventRecord(alloc_done, c.stream));
         ZKM_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
         ZKM_CUDA(cudaEventDestroy(alloc_done));
-        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage] {
+        // AllStark's Arithmetic table handed over as rows comes without its range-check columns (arithmetic_stark.rs:155-192
+        // builds them after the transposition, :127-153): they are generated on the device
+        const int arith_rows_table = (system_id == tables::SYSTEM_ALL_STARK && rows_src[tables::T_ARITHMETIC]) ? tables::T_ARITHMETIC : -1;
+        unsigned* d_bad = (unsigned*)bad_flag.p;
+        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage, arith_rows_table, d_bad] {
             cudaSetDevice(device);
             for (size_t t : order) {
                 size_t n = (size_t)1 << tables[t].log_n;
@@ -267,8 +272,25 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                     // rows as generated (one contiguous block), transposed into column-major on the device
                     e = cudaMemcpyAsync(rows_stage[t], rows_src[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyHostToDevice, cs);
                     if (e == cudaSuccess) {
-                        try { transpose_rows_to_cols(rows_stage[t], dst[t], n, (int)tables[t].ncols, cs); }
-                        catch (const std::exception&) { e = cudaErrorLaunchFailure; }
+                        try {
+                            transpose_rows_to_cols(rows_stage[t], dst[t], n, (int)tables[t].ncols, cs);
+                            if ((int)t == arith_rows_table) {
+                                // rows straight from Operation::to_rows: the range-check columns are generated here
+                                namespace ar = tables::arithmetic;
+                                arith_generate_range_checks(dst[t], n, ar::START_SHARED_COLS, ar::NUM_SHARED_COLS, ar::RANGE_COUNTER,
+                                                            ar::RC_FREQUENCIES, d_bad, cs);
+                                unsigned bad = 0;
+                                e = cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, cs);
+                                if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+                                if (e == cudaSuccess && bad) {
+                                    std::lock_guard<std::mutex> lk(up.mu);
+                                    if (up.error.empty()) up.error = "column value exceeds the max range value 65536";
+                                }
+                            }
+                        } catch (const std::exception& ex) {
+                            std::lock_guard<std::mutex> lk(up.mu);
+                            if (up.error.empty()) up.error = ex.what();
+                        }
                     }
                 } else
                 // small tables (Keccak: 2431 columns of 512 bytes) would cost one driver call per column (~3 us each, 10 ms in

@@ -87,6 +87,10 @@ std::string prof_names();
 // Row-major n x ncols block -> column-major ncols x n (transpose.cu).
 void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cudaStream_t s);
 
+// Arithmetic table (column-major, on the device): fills RANGE_COUNTER and adds the shared columns' histogram to RC_FREQUENCIES.
+void arith_generate_range_checks(u64* cols, size_t n, int first_shared, int num_shared, int counter_col, int freq_col,
+                                 unsigned* d_bad, cudaStream_t s);
+
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 struct PowTable {
     const u64* lo = nullptr;

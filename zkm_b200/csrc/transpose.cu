@@ -32,3 +32,37 @@ void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cud
 }
 
 }  // namespace zkm
+
+// ---- Arithmetic table: range-check columns on the device.
+// Replaces reference arithmetic_stark.rs:127-153 generate_range_checks: RANGE_COUNTER = 0, 1, ..., 2^16 - 1 and then constant,
+// RC_FREQUENCIES[x] += number of cells of the 18 shared columns equal to x.  `bad` is raised if a shared cell is >= 2^16
+// (the reference asserts "column value ... exceeds the max range value").
+namespace zkm {
+
+__global__ void arith_range_counter_kernel(u64* cols, size_t n, int counter_col, u64 range_max) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cols[(size_t)counter_col * n + i] = i < range_max ? (u64)i : range_max - 1;
+}
+__global__ void arith_frequencies_kernel(u64* cols, size_t n, int first_shared, int num_shared, int freq_col, u64 range_max,
+                                         unsigned* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (size_t)num_shared) return;
+    u64 x = cols[(size_t)first_shared * n + i];             // the shared columns are contiguous: column-major block
+    if (x >= range_max) { atomicExch(bad, 1u); return; }
+    atomicAdd((unsigned long long*)&cols[(size_t)freq_col * n + x], 1ULL);
+}
+
+void arith_generate_range_checks(u64* cols, size_t n, int first_shared, int num_shared, int counter_col, int freq_col,
+                                 unsigned* d_bad, cudaStream_t s) {
+    const u64 range_max = 1ull << 16;
+    ZKM_CHECK(n >= range_max, "arithmetic table shorter than the range check (2^16 rows)");
+    ProfScope ps("arith_range_checks", s, 8.0 * (double)n * (num_shared + 2));
+    ZKM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), s));
+    arith_range_counter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cols, n, counter_col, range_max);
+    ZKM_LAUNCHED();
+    size_t cells = n * (size_t)num_shared;
+    arith_frequencies_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(cols, n, first_shared, num_shared, freq_col, range_max, d_bad);
+    ZKM_LAUNCHED();
+}
+
+}  // namespace zkm

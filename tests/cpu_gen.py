@@ -718,7 +718,7 @@ def memory_generate_trace(ops):
     vfc = (a[2][:-1] != a[2][1:]) & ~sfc & ~cfc
     rc = np.where(cfc, a[0][1:] - a[0][:-1] - 1, np.where(sfc, a[1][1:] - a[1][:-1] - 1, np.where(vfc, a[2][1:] - a[2][:-1] - 1,
                                                                                                  a[3][1:] - a[3][:-1])))
-    assert rc.min() >= 0 and rc.max() < n, f"Range check of {rc.max()} is too large. Bug in fill_gaps?"
+    assert rc.size == 0 or (rc.min() >= 0 and rc.max() < n), "Range check is too large. Bug in fill_gaps?"
     t[7, :-1], t[8, :-1], t[9, :-1], t[10, :-1] = cfc, sfc, vfc, rc
     t[11] = np.arange(n, dtype=np.uint64)
     t[12] = np.bincount(t[10].astype(np.int64), minlength=n).astype(np.uint64)

@@ -231,3 +231,36 @@ def test_arithmetic_rows_get_their_range_checks_on_the_device(zkm, orc):
     rows[5, ag.IN2] = 1 << 16                  # not range-checkable
     with pytest.raises(zl.ZkmError, match="exceeds the max range value"):
         zl.prove_with_trace_rows(zkm, [rows] + traces[1:], {0})
+
+
+def test_memory_table_generated_on_the_device(zkm, orc):
+    """zkm_b200_memory_trace (sort, fill_gaps, padding, flags, range check, frequencies on the device) against the restated
+    MemoryStark::generate_trace (tests/cpu_gen.py memory_generate_trace, memory_stark.rs:133-244), bit for bit."""
+    import cpu_gen as cg
+    import cpu_program as cp
+    cases = []
+    image, end = cp.build(with_syscalls=True, sha_blocks=3)
+    cpu = cg.MiniCpu(image, cp.ENTRY, image_id_words=(cp.IMAGE_ID, list(range(1, 10))))
+    while cpu.pc != end:
+        cpu.step()
+    cases.append(cpu.mem_ops)                                   # address gaps between code, data and hash regions
+    rng = np.random.default_rng(9)
+    for n_ops, amax, tmax in ((1, 10, 10), (2, 1 << 20, 5), (64, 50, 1 << 16), (1000, 1 << 24, 1 << 20), (4096, 300, 4000), (5000, 40, 10)):
+        ops = []
+        for i in range(n_ops):
+            seg = int(rng.integers(0, 6))
+            ops.append((int(rng.integers(0, 2)), seg, int(rng.integers(0, 3 if seg == 4 else amax)), int(rng.integers(0, tmax)) * 10,
+                        int(rng.integers(0, 2)), int(rng.integers(0, 1 << 32)), int(rng.integers(0, 2))))
+        cases.append(ops)
+    for ops in cases:
+        want = cg.memory_generate_trace(list(ops))
+        got = zl.memory_trace(zkm, np.array(ops, dtype=np.uint64))
+        assert got.shape == want.shape, (got.shape, want.shape)
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (len(ops), bad[:5], got[:, bad[0][1]], want[:, bad[0][1]])
+    # and the device-generated table drives the AllStark proof like the host-generated one
+    traces, cpu = tr.all_stark_valid_traces(orc, return_cpu=True)
+    dev_mem = zl.memory_trace(zkm, np.array(cpu.mem_ops, dtype=np.uint64))
+    assert (dev_mem == traces[11]).all()
+    proof = zl.prove_with_traces(zkm, traces[:11] + [dev_mem])
+    assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, proof) is None

@@ -258,7 +258,7 @@ def cpu_system_traces():
             cg.memory_generate_trace(cpu.mem_ops)]
 
 
-def all_stark_valid_traces(orc, sha_blocks=0):
+def all_stark_valid_traces(orc, sha_blocks=0, return_cpu=False):
     """A valid trace of all 12 AllStark tables: the test program with its syscalls and the Keccak / SHA-256 precompiles
     (tests/cpu_program.py, with_syscalls), the image-id Poseidon hash of the bootstrap, and every table generated from
     the operations the interpreter logged -- what Traces::into_tables does upstream (witness/traces.rs:230-318)."""
@@ -324,7 +324,7 @@ def all_stark_valid_traces(orc, sha_blocks=0):
             sp[hg.SCS_OUTPUT_STATE + 4 * j:hg.SCS_OUTPUT_STATE + 4 * j + 4] = hg._le4(st[j])
             hg._wadd(sp, hg.SCS_OUTPUT_HX + 6 * j, 2, hx[j], st[j])
         scs_rows.append(sp)
-    return [ag.arithmetic_trace(cpu.arith_ops, 16),
+    out = [ag.arithmetic_trace(cpu.arith_ops, 16),
             cpu.cpu_trace(lg(cpu.clock() + 1)),
             np.ascontiguousarray(p_rows.T),
             hg.rows_to_trace(ps_rows, hg.POSEIDON_SPONGE_COLUMNS, lg(len(ps_rows))),
@@ -336,3 +336,4 @@ def all_stark_valid_traces(orc, sha_blocks=0):
             hg.rows_to_trace(scs_rows, hg.SHA_COMPRESS_SPONGE_COLUMNS, lg(len(scs_rows))),
             logic_trace_from_ops(logic, lg(len(logic))),
             cg.memory_generate_trace(cpu.mem_ops)]
+    return (out, cpu) if return_cpu else out

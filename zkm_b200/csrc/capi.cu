@@ -373,6 +373,21 @@ int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t root
     prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
     ZKM_API_END
 }
+int zkm_b200_memory_trace(const uint64_t* ops, size_t n_ops, uint64_t** cols_out, uint32_t* log_n_out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(ops && cols_out && log_n_out, "null argument");
+    Ctx& c = ctx();
+    DevBuf cols;
+    size_t n = memory_generate_trace_dev(ops, n_ops, cols, c.stream);
+    uint64_t* out = (uint64_t*)malloc(13 * n * sizeof(u64));
+    ZKM_CHECK(out, "out of host memory");
+    cols.download(out, 13 * n);
+    uint32_t lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    *cols_out = out; *log_n_out = lg;
+    ZKM_API_END
+}
+
 int zkm_b200_prove_with_trace_rows(const zkm_table_t* tables, const zkm_table_rows_t* row_tables, const uint32_t* roots_before,
                                    const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
                                    const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err) {

@@ -91,6 +91,9 @@ void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cud
 void arith_generate_range_checks(u64* cols, size_t n, int first_shared, int num_shared, int counter_col, int freq_col,
                                  unsigned* d_bad, cudaStream_t s);
 
+// Memory table from the memory-operation log (memtrace.cu): returns the table height, fills 13 x height columns.
+size_t memory_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevBuf& cols, cudaStream_t s);
+
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 struct PowTable {
     const u64* lo = nullptr;

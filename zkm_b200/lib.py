@@ -32,7 +32,7 @@ EXPORTS = [
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 
@@ -237,6 +237,21 @@ def prove_with_trace_rows(lib, traces, as_rows, roots_before=None, roots_after=N
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)
     return proof
+
+
+def memory_trace(lib, ops):
+    """zkm_b200_memory_trace: ops = (n_ops, 7) uint64 (context, segment, virt, timestamp, is_read, value, filter) in push
+    order -> (13, n) Memory table."""
+    a = np.ascontiguousarray(ops, dtype=np.uint64)
+    assert a.ndim == 2 and a.shape[1] == 7
+    out, lg, err = C.POINTER(C.c_uint64)(), C.c_uint32(), C.c_void_p()
+    lib.zkm_b200_memory_trace.argtypes = [C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint32),
+                                          C.POINTER(C.c_void_p)]
+    check(lib, lib.zkm_b200_memory_trace(a.ctypes.data_as(C.POINTER(C.c_uint64)), a.shape[0], C.byref(out), C.byref(lg), C.byref(err)), err)
+    n = 1 << lg.value
+    t = np.ctypeslib.as_array(out, shape=(13 * n,)).copy().reshape(13, n)
+    lib.zkm_b200_free(out)
+    return t
 
 
 def system_shape(lib, system_id):

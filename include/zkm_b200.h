@@ -133,6 +133,12 @@ int zkm_b200_prove_with_trace_rows(const zkm_table_t tables[12], const zkm_table
  * context, segment, virt, timestamp, is_read, value, filter.  Returns 13 columns (column-major, 2^*log_n_out rows each) in a
  * malloc'ed buffer released with zkm_b200_free -- the Memory entry of tables[] for the calls above. */
 int zkm_b200_memory_trace(const uint64_t* ops, size_t n_ops, uint64_t** cols_out, uint32_t* log_n_out, char** err);
+/* prove_with_trace_rows (row_tables may be NULL: all tables column-major) where the Memory table (index 11) is generated on
+ * the device from the operation log and never crosses PCIe as a table; tables[11] / row_tables[11] are ignored. */
+int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table_rows_t* row_tables, const uint64_t* memory_ops,
+                                   size_t n_memory_ops, const uint32_t roots_before[8], const uint32_t roots_after[8],
+                                   const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
+                                   uint64_t** proof_out, size_t* proof_words, char** err);
 /* Same prover over another System of tables (zkm_b200/csrc/tables/systems.h: 0 = AllStark, 1 = Logic,
  * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory, 5 = Arithmetic, 6 = Keccak+KeccakSponge+Logic+Memory,
  * 7 = Poseidon+PoseidonSponge+Memory, 8 = ShaExtend+ShaExtendSponge+Logic+Memory, 9 = ShaCompress+ShaCompressSponge+

@@ -264,3 +264,6 @@ def test_memory_table_generated_on_the_device(zkm, orc):
     assert (dev_mem == traces[11]).all()
     proof = zl.prove_with_traces(zkm, traces[:11] + [dev_mem])
     assert binding.verify_system(orc, tr.SYSTEM_ALL_STARK, proof) is None
+    # one call: the table is generated on the device and stays there
+    direct = zl.prove_with_memory_ops(zkm, traces, np.array(cpu.mem_ops, dtype=np.uint64))
+    assert _first_diff(direct, proof) is None

@@ -172,13 +172,24 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
 static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t num_tables, const uint64_t* const* d_tables,
                         const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
                         const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
-                        const zkm_table_rows_t* row_tables = nullptr) {
+                        const zkm_table_rows_t* row_tables = nullptr, const uint64_t* mem_ops = nullptr, size_t n_mem_ops = 0) {
     Ctx& c = ctx();
     ZKM_CHECK(tables_in && roots_before && roots_after && cfg && proof_out && proof_words, "null argument");
     // tables given as rows (zkm_b200_prove_with_trace_rows): shape from the row descriptor, data uploaded as one block
     std::vector<zkm_table_t> merged(tables_in, tables_in + num_tables);
     for (uint32_t t = 0; t < num_tables && row_tables; t++)
         if (row_tables[t].rows) { merged[t].cols = nullptr; merged[t].ncols = row_tables[t].ncols; merged[t].log_n = row_tables[t].log_n; }
+    // the Memory table generated on the device from the operation log (zkm_b200_prove_with_memory_ops): never leaves HBM
+    std::vector<char> generated(num_tables, 0);
+    DevBuf generated_memory;
+    if (mem_ops) {
+        ZKM_CHECK(system_id == tables::SYSTEM_ALL_STARK && !d_tables, "memory-operation logs are taken by the AllStark host entry points only");
+        size_t n = memory_generate_trace_dev(mem_ops, n_mem_ops, generated_memory, c.stream);
+        uint32_t lg = 0;
+        while (((size_t)1 << lg) < n) lg++;
+        merged[tables::T_MEMORY].cols = nullptr; merged[tables::T_MEMORY].ncols = 13; merged[tables::T_MEMORY].log_n = lg;
+        generated[tables::T_MEMORY] = 1;
+    }
     const zkm_table_t* tables = merged.data();
     std::vector<DevBuf> row_staging(num_tables);
     DevBuf bad_flag(1, c.stream);              // raised by the device-side Arithmetic range check (rows path)
@@ -201,6 +212,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
             // pageable and, on this platform, also for pinned sources), so table t+1.. stream in while table t is
             // being committed; the prover waits on `ready` before touching a buffer
             const zkm_table_t* tb = &tables[t];
+            if (generated[t]) { in[t].values = std::move(generated_memory); continue; }      // already on the compute stream
             const bool as_rows = row_tables && row_tables[t].rows;
             ZKM_CHECK((tb->cols || as_rows) && tb->ncols > 0, "null/empty table");
             if (!as_rows) for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
@@ -244,6 +256,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
         for (uint32_t t = 0; t < num_tables; t++) bytes[t] = (size_t)tables[t].ncols << tables[t].log_n;
         std::vector<size_t> order = commit_order(bytes);
         up.done.assign(num_tables, 0);
+        for (uint32_t t = 0; t < num_tables; t++) up.done[t] = generated[t];
         up.groups_done.assign(num_tables, 0);
         std::vector<std::vector<int>> gends(num_tables);
         std::vector<std::vector<cudaEvent_t>> gevs(num_tables);
@@ -265,6 +278,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
         up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage, arith_rows_table, d_bad] {
             cudaSetDevice(device);
             for (size_t t : order) {
+                if (!evs[t]) continue;                      // generated on the device: nothing to upload
                 size_t n = (size_t)1 << tables[t].log_n;
                 cudaError_t e = cudaSuccess;
                 size_t g = 0;
@@ -373,6 +387,17 @@ int zkm_b200_prove_with_traces(const zkm_table_t tables[12], const uint32_t root
     prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words);
     ZKM_API_END
 }
+int zkm_b200_prove_with_memory_ops(const zkm_table_t* tables, const zkm_table_rows_t* row_tables, const uint64_t* memory_ops,
+                                   size_t n_memory_ops, const uint32_t* roots_before, const uint32_t* roots_after,
+                                   const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
+                                   uint64_t** proof_out, size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(memory_ops, "null argument");
+    prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words,
+                 row_tables, memory_ops, n_memory_ops);
+    ZKM_API_END
+}
+
 int zkm_b200_memory_trace(const uint64_t* ops, size_t n_ops, uint64_t** cols_out, uint32_t* log_n_out, char** err) {
     ZKM_API_BEGIN
     ZKM_CHECK(ops && cols_out && log_n_out, "null argument");

@@ -32,7 +32,7 @@ EXPORTS = [
     "zkm_b200_commit_values_device", "zkm_b200_batch_free", "zkm_b200_batch_get_coeffs", "zkm_b200_batch_get_lde",
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_families",
 ]
 
 
@@ -233,6 +233,26 @@ def prove_with_trace_rows(lib, traces, as_rows, roots_before=None, roots_after=N
                                                    C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
     rc = lib.zkm_b200_prove_with_trace_rows(carr, rarr, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words),
                                             C.byref(err))
+    check(lib, rc, err)
+    proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+    lib.zkm_b200_free(out)
+    return proof
+
+
+def prove_with_memory_ops(lib, traces, memory_ops, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):
+    """zkm_b200_prove_with_memory_ops: traces[0..10] column-major host tables (traces[11] is ignored), Memory from the log."""
+    cfg = cfg or standard_fast_config(lib)
+    made = [make_table(np.ascontiguousarray(t)) for t in traces[:11]]
+    arr = (Table * 12)(*([m[0] for m in made] + [Table(None, 0, 0)]))
+    ops = np.ascontiguousarray(memory_ops, dtype=np.uint64)
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+    lib.zkm_b200_prove_with_memory_ops.argtypes = [C.POINTER(Table), C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_uint32),
+                                                   C.POINTER(C.c_uint32), C.c_char_p, C.c_uint32, C.POINTER(StarkConfig),
+                                                   C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    rc = lib.zkm_b200_prove_with_memory_ops(arr, None, ops.ctypes.data_as(C.POINTER(C.c_uint64)), ops.shape[0], rb, ra, userdata,
+                                            len(userdata), C.byref(cfg), C.byref(out), C.byref(words), C.byref(err))
     check(lib, rc, err)
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)

@@ -153,11 +153,11 @@ class Segment:
                                               C.byref(self.cfg), C.byref(out), C.byref(words), C.byref(err))
         self._finish(rc, err, out, words)
 
-    def prepare_host(self):
+    def prepare_host(self, pinned=True):
         torch = self.torch
         self.host, made = [], []
         for t, (nc, lg) in enumerate(zip(NCOLS, self.heights)):
-            hbuf = torch.empty(nc << lg, dtype=torch.int64, pin_memory=True)
+            hbuf = torch.empty(nc << lg, dtype=torch.int64, pin_memory=pinned)
             hbuf.copy_(self.dev[t])
             arr = hbuf.numpy().view(np.uint64).reshape(nc, 1 << lg)
             self.host.append(hbuf)
@@ -195,6 +195,11 @@ class Segment:
             ms, la, by, err = C.c_double(), C.c_uint64(), C.c_double(), C.c_void_p()
             self.zl.check(lib, lib.zkm_b200_profile_get(n.encode(), C.byref(ms), C.byref(la), C.byref(by), C.byref(err)), err)
             out[n] = {"ms": ms.value, "launches": la.value, "bytes": by.value}
+            tb = C.c_double()
+            if lib.zkm_b200_profile_get_traffic(n.encode(), C.byref(tb), C.byref(err)) == 0:
+                out[n]["traffic_bytes"] = tb.value
+            else:
+                lib.zkm_b200_free_string(err)
         return out
 
     @staticmethod
@@ -206,29 +211,68 @@ class Segment:
         return None
 
 
-def cpu_pass(workload, ncores, sample_only=False):
-    """CPU arm: the restated oracle (oracle/liborc.so, `kind: port`; the Rust reference cannot be built in this
-    image) running the same full prove_with_traces on a bounded sample of the workload: the same 12 tables
-    with every height above 2^CUT cut to 2^CUT, on all host cores; the time is scaled linearly in trace cells
-    back to the full workload (this favours the CPU: it ignores the log n factor of the transforms)."""
+def host_threads():
+    """Host threads this process may use (the CPU arm runs on all of them)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(workload):
+    """The `config` object of the JSON line: identical in the B200 arm and the reference arm (same workload, same stages)."""
+    heights = workload_log_heights(workload)
+    in_bytes = sum(8 * (nc << lg) for nc, lg in zip(NCOLS, heights))
+    return {"workload": workload, "log_heights": heights, "tables": TABLES,
+            "stages": "full prove_with_traces: 12 tables x (trace commit, CTL/logUp aux, quotient, openings, FRI incl. PoW + 37 queries)",
+            "stark_config": "standard_fast_config: rate_bits 2, cap_height 4, pow_bits 16, 37 queries, 2 challenges, arity 16",
+            "l2": f"inputs {in_bytes / 1e9:.2f} GB per proof > 126 MB L2 (no flush needed)"}
+
+
+def workload_metric(workload):
+    return f"MIPS-segment proofs/sec ({workload}: 2^{max(workload_log_heights(workload))}-row synthetic segment, full STARK prove)"
+
+
+CPU_NOTE = "restated C++ oracle, threaded like the reference's Rayon loops (the Rust reference cannot be built here: no cargo, plonky2 un-vendored)"
+
+
+def _cpu_cache_path(workload, ncores):
+    import socket
+    return pathlib.Path("/tmp") / f"zkm_b200_cpu_arm_{socket.gethostname()}_{workload}_{ncores}.json"
+
+
+def cpu_pass(workload, ncores, tiny=False, use_cache=False):
+    """CPU arm: the restated oracle (oracle/liborc.so, `kind: port`) running the same full prove_with_traces on the FULL
+    workload, once, on `ncores` host threads -- no sampling and no extrapolation.  `tiny` proves the same 12 tables at 2^8
+    rows (untimed warm-up: pages the library and its tables in).  With `use_cache` a figure measured earlier on this host
+    (same workload and thread count; written by every full run) is reused instead of spending minutes of host time again."""
+    import hashlib
     from oracle import binding
+    cache = _cpu_cache_path(workload, ncores)
+    if use_cache and not tiny and cache.exists():
+        try:
+            c = json.loads(cache.read_text())
+            c["sample"] += " [figure reused from this host's earlier run: " + str(cache) + "]"
+            return c
+        except Exception:
+            pass
     orc = binding.load()
     orc.orc_set_threads(ncores)
     full = workload_log_heights(workload)
-    cut = 8 if sample_only else 13
-    sample = [min(h, cut) for h in full]
-    sample[0] = max(sample[0], 16) if not sample_only else sample[0]     # Arithmetic range table needs 2^16 rows
-    cells_full = sum(nc << lg for nc, lg in zip(NCOLS, full))
-    cells_s = sum(nc << lg for nc, lg in zip(NCOLS, sample))
-    traces = synthetic_traces_host(sample)
+    heights = [min(h, 8) for h in full] if tiny else full
+    traces = synthetic_traces_host(heights)
     t0 = time.perf_counter()
-    binding.prove_system(orc, 0, traces)
+    proof = binding.prove_system(orc, 0, traces)
     dt = time.perf_counter() - t0
-    scale = cells_full / cells_s
-    return {"value": 1.0 / (dt * scale), "unit": "proofs/s",
-            "metric": f"MIPS-segment proofs/sec ({workload}: 2^{max(full)}-row synthetic segment, full STARK prove)",
-            "sample": f"full prove at heights {sample} ({dt:.2f} s on {ncores} threads), scaled x{scale:.2f} linearly in trace cells to {workload}",
-            "note": "restated C++ oracle (the Rust reference cannot be built here: no cargo, plonky2 un-vendored)"}
+    out = {"value": 1.0 / dt, "unit": "proofs/s", "seconds": dt, "metric": workload_metric(workload),
+           "sample": f"full: one complete proof at heights {heights} in {dt:.1f} s on {ncores} threads, nothing extrapolated",
+           "proof_sha256": hashlib.sha256(proof.tobytes()).hexdigest(), "note": CPU_NOTE}
+    if not tiny:
+        try:
+            cache.write_text(json.dumps(out))
+        except Exception:
+            pass
+    return out
 
 
 def synthetic_traces_host(log_heights, seed=0x5EED000000000000):
@@ -321,26 +365,24 @@ def run_n22(args):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The Rust reference cannot be
-    built in this image (no cargo; plonky2 un-vendored — DESIGN.md), so this times the restated C++
-    oracle on all host cores, on a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path.  The Rust reference cannot be built in this image
+    (no cargo; plonky2 un-vendored -- DESIGN.md), so this times the restated C++ oracle on all host cores, on the SAME
+    workload as the B200 arm: one full proof (a U20 proof is minutes of host time, so exactly one is timed whatever --steps
+    says; the line reports the steps actually run)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
-    for _ in range(args.warmup and 1):
-        cpu_pass(args.workload, ncores, sample_only=True)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_pass(args.workload, ncores, sample_only=False))
-    best = max(v["value"] for v in vals)
-    info = vals[0]
-    line = {"impl": "reference", "metric": info["metric"], "value": best, "unit": info["unit"], "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / best if best else None,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)",
-            "data": "synthetic", "config": {"workload": args.workload, "note": info["note"]},
-            "cpu_baseline": {"value": best, "unit": info["unit"], "cores": ncores, "kind": "port", "sample": info["sample"]},
-            "e2e": {"value": best, "unit": info["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    ncores = host_threads()
+    if args.warmup:
+        cpu_pass(args.workload, ncores, tiny=True)
+    r = cpu_pass(args.workload, ncores)
+    line = {"impl": "reference", "metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": args.gpus,
+            "steps": 1, "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": 1000.0 * r["seconds"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks)", "data": "synthetic", "config": workload_config(args.workload),
+            "cpu_baseline": {"value": r["value"], "unit": r["unit"], "cores": ncores, "kind": "port", "sample": r["sample"],
+                             "note": r["note"], "proof_sha256": r["proof_sha256"]},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -375,7 +417,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="U20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workers", type=int, default=0, help="proofs in flight per GPU (worker contexts); 0 = 3, fewer on small hosts")
+    ap.add_argument("--workers", type=int, default=0, help="proofs in flight per GPU (worker contexts); 0 = 3")
+    ap.add_argument("--host-memory", default="pinned", choices=["pinned", "pageable"],
+                    help="e2e leg: where the caller's trace columns live (the reference's Vec<F> columns are pageable)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -399,7 +443,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = zl.init(local)
     # measured on one B200 (profiles/r1c_workers_sweep.txt): 1 worker 2.88, 2: 2.99, 3: 3.16, 4: 3.20 proofs/s
-    NW = args.workers if args.workers > 0 else max(1, min(3, (os.cpu_count() or 2) // (2 * max(1, world))))
+    # the same number of proofs in flight per GPU at every N (each worker is one mostly-blocked host thread + its uploader)
+    NW = args.workers if args.workers > 0 else (3 if host_threads() >= 4 else 1)
     # one synthetic segment per worker context: NW proofs are in flight on this GPU at any time (one host thread, one pair of
     # streams and one arena each, include/zkm_b200.h "Worker contexts"); a step = NW segments, one per worker
     segs = [Segment(lib, args.workload, seed_offset=rank * NW + i, rank=rank, world=world) for i in range(NW)]
@@ -478,7 +523,7 @@ def main():
     lib.zkm_b200_profile_enable(0)
     # ---- end to end through the C ABI with host buffers ----
     for sg in segs:
-        sg.prepare_host()
+        sg.prepare_host(pinned=args.host_memory == "pinned")
 
     def gather_all():
         if world > 1:                            # the path's only exchange: finished proofs gathered on rank 0 (NCCL)
@@ -501,47 +546,59 @@ def main():
         peak, peak_kind = peaks()
         total_ms = sum(v["ms"] for v in fam.values()) or 1.0
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-        # the roofline entry is reported for the HBM-bound NTT family (BASELINE.json: "NTT GB/s vs HBM peak"); the
-        # dominant family (Poseidon leaf hashing, integer-ALU bound) is named next to it with every family's share
-        ntt = fam.get("ntt_pass", top[1])
-        ach = ntt["bytes"] / (ntt["ms"] * 1e-3) / 1e9 if ntt["ms"] else 0.0
         value = args.steps * NW * world / (t_dev * 1e-3)
         e2e = args.steps * NW * world / (t_e2e * 1e-3)
-        line = {"metric": seg.metric, "value": value, "unit": seg.unit, "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": t_dev / args.steps, "ms_per_step_instrumented": t_prof / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None,
+
+        def roof(name, v, note):
+            """achieved = algorithmic bytes of the family's launches / their device time (CUDA events on
+            the launching stream), against the measured copy peak; `traffic` = DRAM bytes per launch from the committed
+            `ncu --set full` capture."""
+            ach = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0
+            r = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                 "peak_kind": peak_kind, "traffic": seg.ncu_traffic(name), "launches": v["launches"],
+                 "avg_launch_ms": v["ms"] / max(1, v["launches"]), "share_of_step": v["ms"] / total_ms,
+                 "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"]), "note": note}
+            if v.get("traffic_bytes"):
+                r["pass_traffic_GBps"] = v["traffic_bytes"] / (v["ms"] * 1e-3) / 1e9
+                r["pass_traffic_frac"] = r["pass_traffic_GBps"] / peak
+            return r
+        notes = {"leaf_hash": "Poseidon leaf hashing: 8 B per column per leaf against ~18 000 instructions per permutation -- "
+                              "issue-bound integer/FP64 kernel, its HBM fraction is tiny by construction (DESIGN.md section 3 "
+                              "gives the pipe-level bound; `poseidon` below gives permutations/s)",
+                 "ntt_pass": "algorithmic bytes per SURVEY 8(d): 16*N*C per plain transform, 48*n*C per iNTT + 4x coset LDE "
+                             "(the LDE's re-read of the fresh coefficients is not counted); pass_traffic counts the 16 B per "
+                             "element every shared-memory pass moves"}
+        line = {"metric": workload_metric(args.workload), "value": value, "unit": seg.unit, "n_gpus": world, "steps": args.steps,
+                "warmup": W, "ms_per_step": t_dev / args.steps, "ms_per_step_instrumented": t_prof / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 (Goldilocks)", "data": "synthetic",
-                "config": {"workload": args.workload, "stages": seg.stages, "log_heights": seg.heights,
-                           "l2": f"inputs {seg.input_bytes / 1e9:.2f} GB per step > 126 MB L2 (no flush needed)",
-                           "segments_per_step": NW, "numa_binding": numa,
+                "config": workload_config(args.workload),
+                "launch": {"segments_per_step": NW, "numa_binding": numa,
                            "parallelism": f"{world} GPU(s) x {NW} worker contexts, one independent segment each (a step = "
                                           f"{NW * world} proofs)"},
                 "e2e": {"value": e2e, "unit": seg.unit, "ms_per_step": t_e2e / args.steps,
-                        "h2d_bytes_per_step": seg.input_bytes * NW, "d2h_bytes_per_step": seg.output_bytes * NW},
+                        "h2d_bytes_per_step": seg.input_bytes * NW, "d2h_bytes_per_step": seg.output_bytes * NW,
+                        "host_memory": args.host_memory},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "ntt_pass_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "peak_kind": peak_kind, "traffic": seg.ncu_traffic("ntt_pass"),
-                             "launches": ntt["launches"], "avg_launch_ms": ntt["ms"] / max(1, ntt["launches"]),
-                             "share_of_step": ntt["ms"] / total_ms},
+                "roofline": roof(top[0], top[1], notes.get(top[0], "")),
+                "dominant_family": top[0],
                 "kernel_families": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                                         "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0),
                                         "share": v["ms"] / total_ms} for k, v in fam.items()},
-                "dominant_family": top[0],
-                # the same figures for the family that dominates the step (Poseidon leaf hashing: FP64/ALU issue bound, its
-                # HBM fraction is tiny by construction: 8 B per column per leaf against ~18 500 instructions per permutation)
-                "roofline_dominant": {"bound": "hbm", "kernel": top[0],
-                                      "achieved": top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9 if top[1]["ms"] else 0.0,
-                                      "peak": peak, "unit": "GB/s",
-                                      "frac": (top[1]["bytes"] / (top[1]["ms"] * 1e-3) / 1e9 / peak) if top[1]["ms"] else 0.0,
-                                      "traffic": seg.ncu_traffic(top[0]), "launches": top[1]["launches"],
-                                      "avg_launch_ms": top[1]["ms"] / max(1, top[1]["launches"]),
-                                      "share_of_step": top[1]["ms"] / total_ms,
-                                      "note": "issue-bound integer/FP64 kernel; see DESIGN.md section 3 for the pipe-level bound"},
                 "clocks": clk.summary()}
+        if "ntt_pass" in fam:
+            line["roofline_ntt"] = roof("ntt_pass", fam["ntt_pass"], notes["ntt_pass"])
+        hashing = [fam[k] for k in ("leaf_hash", "merkle_levels", "leaf_hash_rows") if k in fam]
+        if hashing:
+            perms = sum(v.get("traffic_bytes", 0.0) for v in hashing)          # hashing families report permutations there
+            t_hash = sum(v["ms"] for v in hashing)
+            line["poseidon"] = {"permutations_per_step": perms / args.steps, "Gperm_per_s": perms / (t_hash * 1e-3) / 1e9 if t_hash else 0.0,
+                                "share_of_step": t_hash / total_ms}
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_pass(args.workload, os.cpu_count() or 1, sample_only=False)
-            line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": cb["sample"]}
+            nc = host_threads()
+            cb = cpu_pass(args.workload, nc, use_cache=True)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": nc, "kind": "port",
+                                    "sample": cb["sample"], "note": cb["note"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -79,6 +79,9 @@ int zkm_b200_timer_stop(double* ms, char** err);
 void zkm_b200_profile_enable(int on);
 int zkm_b200_profile_reset(char** err);
 int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, double* bytes, char** err);
+/* Second per-family counter: bytes moved by the shared-memory passes for "ntt_pass" (16 B per element per pass), Poseidon
+ * permutations for the hashing families ("leaf_hash", "merkle_levels", "leaf_hash_rows"), 0 elsewhere. */
+int zkm_b200_profile_get_traffic(const char* family, double* aux, char** err);
 char* zkm_b200_profile_families(void);
 
 /* ---- the prover --------------------------------------------------------------------------------

@@ -99,3 +99,51 @@ def test_error_reporting(zkm):
     rc = zkm.zkm_b200_ntt(u64ptr(buf), 1, 3, 9, C.byref(err))
     assert rc == -1 and err.value
     zkm.zkm_b200_free_string(err)
+
+
+@pytest.mark.parametrize("log_n", [20, 22])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ntt_full_size_matches_oracle(zkm, orc, log_n, kind):
+    """BASELINE config #2 / #3 row counts (2^20, 2^22): fft, ifft and coset_ifft(7) of two columns, every output word
+    compared with the oracle's transform (round trips and linearity alone would survive a consistent index permutation)."""
+    cols = random_columns(2, 1 << log_n, seed=2000 + log_n)
+    a = cols.copy(); b = cols.copy()
+    err = C.c_void_p()
+    _chk(zkm, zkm.zkm_b200_ntt(u64ptr(a), 2, log_n, kind, C.byref(err)), err)
+    orc.orc_ntt(u64ptr(b), 2, log_n, kind)
+    assert (a == b).all()
+
+
+@pytest.mark.parametrize("ncols,log_n", [(9, 20), (3, 22)])
+def test_commit_full_size_matches_oracle(zkm, orc, ncols, log_n):
+    """PolynomialBatch::from_values at the benchmark row counts: Merkle cap, coefficients, the whole 4n-point LDE of the
+    first and last column, leaf rows and authentication paths, all against the oracle."""
+    n = 1 << log_n
+    cols = random_columns(ncols, n, seed=77 + log_n)
+    cap_g = np.zeros(64, dtype=np.uint64); cap_o = np.zeros(64, dtype=np.uint64)
+    t, keep = zl.make_table(cols)
+    h = C.c_void_p(); err = C.c_void_p()
+    _chk(zkm, zkm.zkm_b200_commit_values(C.byref(t), 2, 4, C.byref(h), u64ptr(cap_g), C.byref(err)), err)
+    ho = orc.orc_commit(col_ptrs(cols), ncols, log_n, 2, 4, 1, u64ptr(cap_o))
+    assert ho
+    try:
+        assert (cap_g == cap_o).all()
+        for c in (0, ncols - 1):
+            cg = np.zeros(n, dtype=np.uint64); co = np.zeros(n, dtype=np.uint64)
+            _chk(zkm, zkm.zkm_b200_batch_get_coeffs(h, c, u64ptr(cg), C.byref(err)), err)
+            orc.orc_batch_get_coeffs(ho, c, u64ptr(co))
+            assert (cg == co).all()
+            lg = np.zeros(4 * n, dtype=np.uint64); lo = np.zeros(4 * n, dtype=np.uint64)
+            _chk(zkm, zkm.zkm_b200_batch_get_lde(h, c, u64ptr(lg), C.byref(err)), err)
+            orc.orc_batch_get_lde(ho, c, u64ptr(lo))
+            assert (lg == lo).all()
+        plen = log_n + 2 - 4
+        for leaf in (0, 1, 4 * n - 1, (4 * n) // 3, 2 * n + 12345):
+            rg = np.zeros(ncols, dtype=np.uint64); ro = np.zeros(ncols, dtype=np.uint64)
+            sg = np.zeros(plen * 4, dtype=np.uint64); so = np.zeros(plen * 4, dtype=np.uint64)
+            _chk(zkm, zkm.zkm_b200_batch_open(h, leaf, u64ptr(rg), u64ptr(sg), C.byref(err)), err)
+            orc.orc_batch_open(ho, leaf, u64ptr(ro), u64ptr(so))
+            assert (rg == ro).all() and (sg == so).all()
+    finally:
+        zkm.zkm_b200_batch_free(h)
+        orc.orc_batch_free(ho)

@@ -122,6 +122,23 @@ def test_all_stark_synthetic_proof_equals_oracle_mid_heights(zkm, orc):
     assert _first_diff(gpu, cpu) is None
 
 
+@pytest.mark.parametrize("workload", ["U18", "U20"])
+def test_all_stark_benchmark_config_equals_oracle(zkm, orc, workload):
+    """The configuration bench.py reports (Arithmetic/Cpu/Memory at 2^20 rows, Logic 2^18, the other
+    tables 2^6; U18 is the same shape at a quarter of the rows): the GPU proof through zkm_b200_prove_with_traces (host
+    columns, the drop-in call) equals the oracle's proof of the same traces word for word.  One oracle proof at U20 takes a few
+    minutes of host time; nothing is sampled or extrapolated."""
+    import hashlib
+    import bench
+    heights = bench.workload_log_heights(workload)
+    traces = zl.synth_traces(zkm, tr.SYSTEM_ALL_STARK, heights)
+    gpu = zl.prove_with_traces(zkm, traces)
+    orc.orc_set_threads(bench.host_threads())
+    cpu = binding.prove_system(orc, tr.SYSTEM_ALL_STARK, traces)
+    assert _first_diff(gpu, cpu) is None
+    assert hashlib.sha256(gpu.tobytes()).hexdigest() == hashlib.sha256(cpu.tobytes()).hexdigest()
+
+
 def test_all_stark_valid_trace_proof_verifies(zkm, orc):
     """The drop-in entry point on a VALID 12-table trace (MIPS program with syscalls and the Keccak / SHA-256 / Poseidon
     precompiles, tests/traces.py all_stark_valid_traces): the GPU proof is accepted by the restated verifier

@@ -12,21 +12,26 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = pathlib.Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
-OBJ = ROOT / "build"
-LIB = ROOT / "libzkm_b200.so"
+# A/B builds for tuning runs: ZKM_BUILD_TAG=x ZKM_EXTRA_NVCC="-DFOO=1" python -m zkm_b200.build  ->  libzkm_b200_x.so, which
+# zkm_b200.lib loads instead of the product library when ZKM_B200_LIB_TAG=x is set.  The product build uses neither.
+TAG = os.environ.get("ZKM_BUILD_TAG", "")
+OBJ = ROOT / ("build_" + TAG if TAG else "build")
+LIB = ROOT / (f"libzkm_b200_{TAG}.so" if TAG else "libzkm_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("ZKM_EXTRA_NVCC", "").split()
 
 
 def _deps_hash(src: pathlib.Path) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(src.read_bytes())
-    for p in sorted(list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.h")) + [ROOT.parent / "include/zkm_b200.h"]):
+    # quotient_p1..3.cu #include "quotient.cu": sources that include other sources depend on every .cu as well
+    extra = list(CSRC.glob("*.cu")) if b'.cu"' in src.read_bytes() else []
+    for p in sorted(list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.h")) + [ROOT.parent / "include/zkm_b200.h"] + extra):
         h.update(p.read_bytes())
     return h.hexdigest()
 

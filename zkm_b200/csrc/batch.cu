@@ -1,6 +1,9 @@
 #include "batch.cuh"
 #include <memory>
 #include <map>
+#include <mutex>
+#include <atomic>
+#include <algorithm>
 
 namespace zkm {
 
@@ -9,43 +12,77 @@ static std::unique_ptr<Ctx> g_ctx;
 // can be in flight on one device (the latency-bound phases of one overlap the throughput-bound kernels of the other).
 static thread_local Ctx* t_ctx = nullptr;
 
-// ---- arena (dev.cuh): one per context, because a freed block is handed to the next user on the SAME stream only
+// ---- arena (dev.cuh): one per context, because a freed block is handed to the next user on the SAME stream only.
+// All arenas are registered so that a failed cudaMalloc can give back the idle blocks cached by EVERY context (with several
+// proofs in flight the sibling workers' caches would otherwise stay pinned while this one runs out of memory), and the bytes
+// cached device-wide are capped at half of the device memory whatever the number of contexts.
 struct Arena {
+    std::mutex mu;                                  // the owner thread allocates/frees; any thread may trim
     std::multimap<size_t, void*> free_blocks;       // size -> block
     size_t cached = 0, live = 0;
 };
 namespace {
+std::mutex g_arenas_mu;
+std::vector<Arena*>& all_arenas() { static std::vector<Arena*>* v = new std::vector<Arena*>(); return *v; }
+std::atomic<size_t> g_cached_total{0};
+size_t g_cache_limit = (size_t)64 << 30;           // set from the device size in ctx_init
+Arena* arena_new() {
+    Arena* a = new Arena();
+    std::lock_guard<std::mutex> g(g_arenas_mu);
+    all_arenas().push_back(a);
+    return a;
+}
+void arena_unregister(Arena* a) {
+    std::lock_guard<std::mutex> g(g_arenas_mu);
+    auto& v = all_arenas();
+    v.erase(std::remove(v.begin(), v.end(), a), v.end());
+}
 // heap-allocated and never destroyed: DevBufs owned by other statics may be released during process exit
-Arena& g_arena0 = *new Arena();
-const size_t ARENA_CACHE_LIMIT = (size_t)150 << 30;
+Arena& g_arena0 = *arena_new();
 Arena& cur_arena() { return (t_ctx && t_ctx->arena) ? *t_ctx->arena : g_arena0; }
-void arena_trim_one(Arena& a) {
-    cudaDeviceSynchronize();
+// cached blocks are idle by construction (their last user's kernels may still be running: hence the device synchronisation)
+void arena_trim_locked(Arena& a) {
     for (auto& kv : a.free_blocks) cudaFree(kv.second);
+    g_cached_total -= a.cached;
     a.free_blocks.clear();
     a.cached = 0;
+}
+void arena_trim_one(Arena& a) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> g(a.mu);
+    arena_trim_locked(a);
+}
+void arena_trim_all() {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> g(g_arenas_mu);
+    for (Arena* a : all_arenas()) { std::lock_guard<std::mutex> ga(a->mu); arena_trim_locked(*a); }
 }
 }
 void* arena_alloc(size_t bytes) {
     Arena& A = cur_arena();
     bytes = (bytes + 511) & ~(size_t)511;
-    auto it = A.free_blocks.lower_bound(bytes);
-    // reuse a cached block when it is not wastefully larger than the request
-    if (it != A.free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
-        void* p = it->second;
-        A.cached -= it->first;
-        A.live += it->first;
-        A.free_blocks.erase(it);
-        return p;
+    {
+        std::lock_guard<std::mutex> g(A.mu);
+        auto it = A.free_blocks.lower_bound(bytes);
+        // reuse a cached block when it is not wastefully larger than the request
+        if (it != A.free_blocks.end() && it->first <= bytes + bytes / 8 + 4096) {
+            void* p = it->second;
+            A.cached -= it->first;
+            g_cached_total -= it->first;
+            A.live += it->first;
+            A.free_blocks.erase(it);
+            return p;
+        }
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        arena_trim_one(A);                         // give cached blocks back and retry once
+        arena_trim_all();                          // give every context's cached blocks back and retry once
         e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> g(A.mu);
     A.live += bytes;
     return p;
 }
@@ -53,15 +90,17 @@ void arena_free(void* p, size_t bytes) {
     if (!p) return;
     Arena& A = cur_arena();
     bytes = (bytes + 511) & ~(size_t)511;
+    if (g_cached_total.load() + bytes > g_cache_limit) arena_trim_one(A);
+    std::lock_guard<std::mutex> g(A.mu);
     // blocks handed out from the cache may be larger than the request; the size recorded here is the request rounded up,
     // which is what lower_bound matched against, so re-insert under that size (never larger than the real block)
     A.live -= bytes <= A.live ? bytes : A.live;
-    if (A.cached + bytes > ARENA_CACHE_LIMIT) arena_trim_one(A);
     A.free_blocks.emplace(bytes, p);
     A.cached += bytes;
+    g_cached_total += bytes;
 }
 void arena_trim() { arena_trim_one(cur_arena()); }
-size_t arena_cached_bytes() { return cur_arena().cached; }
+size_t arena_cached_bytes() { Arena& A = cur_arena(); std::lock_guard<std::mutex> g(A.mu); return A.cached; }
 
 bool ctx_ready() { return (bool)g_ctx; }
 Ctx& ctx() {
@@ -81,6 +120,7 @@ void ctx_init(int device) {
     cudaDeviceProp prop;
     ZKM_CUDA(cudaGetDeviceProperties(&prop, device));
     ZKM_CHECK(prop.major >= 10, "zkm_b200: kernels are built for sm_100a (Blackwell) only");
+    g_cache_limit = prop.totalGlobalMem / 2;
     auto c = std::make_unique<Ctx>();
     c->device = device;
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -92,7 +132,7 @@ Ctx* worker_create() {
     ZKM_CUDA(cudaSetDevice(g_ctx->device));
     auto c = std::make_unique<Ctx>();
     c->device = g_ctx->device;
-    c->arena = new Arena();
+    c->arena = arena_new();
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ZKM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     return c.release();
@@ -112,6 +152,7 @@ void worker_destroy(Ctx* w) {
     delete w;                                      // ~NttTables releases its buffers while t_ctx still names this context
     t_ctx = (prev == w) ? nullptr : prev;
     arena_trim_one(*a);
+    arena_unregister(a);
     delete a;
     cudaStreamDestroy(s0);
     cudaStreamDestroy(s1);

@@ -107,6 +107,13 @@ int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, dou
     if (!ok) throw std::runtime_error(std::string("no such kernel family: ") + family);
     ZKM_API_END
 }
+int zkm_b200_profile_get_traffic(const char* family, double* aux, char** err) {
+    ZKM_API_BEGIN
+    double a = 0;
+    if (!prof_get(family, nullptr, nullptr, nullptr, &a)) throw std::runtime_error(std::string("no such kernel family: ") + family);
+    if (aux) *aux = a;
+    ZKM_API_END
+}
 char* zkm_b200_profile_families(void) {
     std::string n;
     try { n = prof_names(); } catch (...) {}
@@ -199,6 +206,16 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
     sc.num_challenges = cfg->num_challenges; sc.arity_bits = cfg->arity_bits; sc.final_poly_bits = cfg->final_poly_bits;
     std::vector<TableInput> in(num_tables);
     auto T0 = std::chrono::steady_clock::now();
+    // declared before the per-table loop below so that an exception thrown there still destroys the events created so far
+    struct Uploader {
+        std::thread th; std::mutex mu; std::condition_variable cv; std::vector<char> done; std::vector<int> groups_done;
+        std::string error;
+        ~Uploader() { if (th.joinable()) th.join(); }
+    } up;
+    struct EventGuard {
+        std::vector<TableInput>& v; cudaStream_t cs; Uploader& u;
+        ~EventGuard() { if (u.th.joinable()) u.th.join(); cudaStreamSynchronize(cs); for (auto& x : v) { if (x.ready) cudaEventDestroy(x.ready); for (cudaEvent_t e : x.group_ready) if (e) cudaEventDestroy(e); } }
+    } guard{in, c.copy_stream, up};
     for (uint32_t t = 0; t < num_tables; t++) {
         in[t].ncols = tables[t].ncols; in[t].log_n = tables[t].log_n;
         ZKM_CHECK(tables[t].log_n <= 26, "trace too long");
@@ -234,15 +251,6 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
             }
         }
     }
-    struct Uploader {
-        std::thread th; std::mutex mu; std::condition_variable cv; std::vector<char> done; std::vector<int> groups_done;
-        std::string error;
-        ~Uploader() { if (th.joinable()) th.join(); }
-    } up;
-    struct EventGuard {
-        std::vector<TableInput>& v; cudaStream_t cs; Uploader& u;
-        ~EventGuard() { if (u.th.joinable()) u.th.join(); cudaStreamSynchronize(cs); for (auto& x : v) { if (x.ready) cudaEventDestroy(x.ready); for (cudaEvent_t e : x.group_ready) if (e) cudaEventDestroy(e); } }
-    } guard{in, c.copy_stream, up};
     if (!d_tables) {
         int device = c.device;
         cudaStream_t cs = c.copy_stream;

@@ -73,14 +73,16 @@ struct DevBuf {
 // zkm_b200_profile_enable.  Scope names follow the kernel families listed in DESIGN.md; bench.py
 // reads them back for the roofline entry.  Disabled: zero overhead beyond one branch.
 struct ProfScope {
-    const char* name; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; double bytes;
-    ProfScope(const char* name_, cudaStream_t s_, double algorithmic_bytes = 0);
+    const char* name; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; double bytes, aux;
+    // algorithmic_bytes: SURVEY section 8(d) accounting (inputs read once + outputs written once); aux: a second per-family
+    // counter -- bytes moved by the shared-memory passes for the NTT family, Poseidon permutations for the hashing families
+    ProfScope(const char* name_, cudaStream_t s_, double algorithmic_bytes = 0, double aux = 0);
     ~ProfScope();
 };
 void prof_enable(bool on);
 void prof_reset();
 // Resolves pending events (synchronises) and returns totals for one family; false if never seen.
-bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes);
+bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes, double* aux = nullptr);
 // Names seen so far, '\n'-separated.
 std::string prof_names();
 

@@ -198,9 +198,8 @@ void fri_reduce_batches(const Batch& trace, const Batch& aux, const Batch& quot,
 
 void fri_combine(const u64* d_r, int log_n, gl2 zeta, gl2 zeta_next, gl2 v0, gl2 v1, gl2 v2, gl2 a0, gl2 a1, u64* d_out, cudaStream_t s) {
     size_t n = (size_t)1 << log_n;
-    auto tab = make_pow_table(gl_root_of_unity(log_n), log_n, s);
     CombineParams p;
-    p.r = d_r; p.n = n; p.wn = tab->view;
+    p.r = d_r; p.n = n; p.wn = ntt_root_table(ctx().ntt, log_n, 0, s);      // cached per context
     p.zeta[0] = zeta.a.v; p.zeta[1] = zeta.b.v; p.zeta_next[0] = zeta_next.a.v; p.zeta_next[1] = zeta_next.b.v;
     p.v0[0] = v0.a.v; p.v0[1] = v0.b.v; p.v1[0] = v1.a.v; p.v1[1] = v1.b.v; p.v2[0] = v2.a.v; p.v2[1] = v2.b.v;
     p.a0[0] = a0.a.v; p.a0[1] = a0.b.v; p.a1[0] = a1.a.v; p.a1[1] = a1.b.v;
@@ -208,7 +207,6 @@ void fri_combine(const u64* d_r, int log_n, gl2 zeta, gl2 zeta_next, gl2 v0, gl2
     ProfScope ps("fri_combine", s, 64.0 * (double)n);
     fri_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
     ZKM_LAUNCHED();
-    ZKM_CUDA(cudaStreamSynchronize(s));
 }
 
 void fri_leaf_rows(const u64* d_lde, size_t col_stride, int log_nr, int rate_bits, int arity_bits, u64* d_rows, cudaStream_t s) {

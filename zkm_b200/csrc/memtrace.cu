@@ -90,31 +90,40 @@ __device__ __forceinline__ void put_row(u64* cols, size_t n2, size_t r, const Me
     cols[C_FILTER * n2 + r] = m.filter; cols[C_TS * n2 + r] = m.ts; cols[C_IS_READ * n2 + r] = m.is_read;
     cols[C_CTX * n2 + r] = m.ctx; cols[C_SEG * n2 + r] = m.seg; cols[C_VIRT * n2 + r] = m.virt; cols[C_VALUE * n2 + r] = value;
 }
-// places every sorted operation, its dummy reads and (after the last element of the pre-padding list) the padding rows
+// One thread per OUTPUT row: row r belongs to the sorted operation i with the largest start position pos(i) <= r (binary
+// search over the monotone positions pos(i) = i + scan[i] + (i > last_gap ? pad : 0)); offset 0 is the operation itself,
+// offsets 1..gaps[i] are its fill_gaps dummy reads, and the rows after those (only behind the last element of the pre-padding
+// list) are padding copies.  Every row is written by its own thread, coalesced per column, so neither a long padding tail
+// (up to n2/2 rows) nor a huge address gap serialises in one thread.
+__device__ __forceinline__ size_t mem_row_pos(const u64* scan, size_t i, long long last_gap, size_t pad) {
+    return i + scan[i] + ((last_gap >= 0 && (long long)i > last_gap) ? pad : 0);
+}
 __global__ void mem_place_kernel(const u64* ops, const Key* keys, const u64* gaps, const u64* scan, size_t n_ops, u64 max_rc,
                                  long long last_gap, size_t pad, size_t n2, u64* cols) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ops) return;
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n2) return;
+    size_t lo = 0, hi = n_ops - 1;                      // pos(0) = 0 <= r
+    while (lo < hi) {
+        size_t mid = (lo + hi + 1) >> 1;
+        if (mem_row_pos(scan, mid, last_gap, pad) <= r) lo = mid; else hi = mid - 1;
+    }
+    const size_t i = lo;
+    const u64 j = r - mem_row_pos(scan, i, last_gap, pad);
     const u64* o = ops + 7 * (keys[i].lo & 0xFFFFFF);
     MemRow m = {o[6], o[3], o[4], o[0], o[1], o[2], o[5]};
-    const bool has_gaps = last_gap >= 0;
-    size_t pos = i + scan[i] + ((has_gaps && (long long)i > last_gap) ? pad : 0);
-    put_row(cols, n2, pos, m);
+    if (j == 0) { put_row(cols, n2, r, m); return; }
     const u64 g = gaps[i];
     MemRow d = m;
     d.filter = 0; d.is_read = 1;
-    if (g) {
-        const u64* b = ops + 7 * (keys[i + 1].lo & 0xFFFFFF);
-        const bool virt_gap = o[2] != b[2];
-        for (u64 j = 1; j <= g; j++) {
-            if (virt_gap) { d.virt = m.virt + j * (max_rc + 1); d.ts = 0; d.value = 0; }
-            else d.ts = m.ts + j * max_rc;
-            put_row(cols, n2, pos + j, d);
-        }
+    // dummy number jj of this operation (padding = copies of the last element of the list before padding: the last dummy
+    // pushed if there is one, else the last sorted operation as a filtered-off read)
+    const u64 jj = j <= g ? j : g;
+    if (jj) {
+        const u64* nx = ops + 7 * (keys[i + 1].lo & 0xFFFFFF);
+        if (o[2] != nx[2]) { d.virt = m.virt + jj * (max_rc + 1); d.ts = 0; d.value = 0; }
+        else d.ts = m.ts + jj * max_rc;
     }
-    // padding = copies of the last element of the list before padding: the last dummy pushed, else the last sorted operation
-    if (has_gaps ? (long long)i == last_gap : i + 1 == n_ops)
-        for (size_t j = 1; j <= pad; j++) put_row(cols, n2, pos + g + j, d);
+    put_row(cols, n2, r, d);
 }
 __global__ void mem_flags_kernel(u64* cols, size_t n2, unsigned* bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,8 +148,9 @@ size_t memory_generate_trace_dev(const u64* h_ops, size_t n_ops, DevBuf& cols, c
     ZKM_CHECK(n_ops < ((size_t)1 << 24), "too many memory operations");
     for (size_t i = 0; i < n_ops; i++) {
         const u64* o = h_ops + 7 * i;
-        ZKM_CHECK(o[0] < (1ull << 24) && o[1] < 256 && o[2] < (1ull << 32) && o[3] < (1ull << 40) && o[4] <= 1 && o[6] <= 1,
-                  "memory operation out of range");
+        // value: the reference stores it with from_canonical_u32 (memory_stark.rs:62-72)
+        ZKM_CHECK(o[0] < (1ull << 24) && o[1] < 256 && o[2] < (1ull << 32) && o[3] < (1ull << 40) && o[4] <= 1 && o[5] < (1ull << 32) &&
+                  o[6] <= 1, "memory operation out of range");
     }
     size_t n1 = 1;
     while (n1 < n_ops) n1 <<= 1;
@@ -170,7 +180,7 @@ size_t memory_generate_trace_dev(const u64* h_ops, size_t n_ops, DevBuf& cols, c
     while (n2 < n_list) n2 <<= 1;
     cols.alloc((size_t)MEM_COLS * n2, s);
     cols.zero();
-    mem_place_kernel<<<(unsigned)((n_ops + th - 1) / th), th, 0, s>>>(ops.p, k, gaps.p, scan.p, n_ops, max_rc, last_gap, n2 - n_list, n2, cols.p);
+    mem_place_kernel<<<(unsigned)((n2 + th - 1) / th), th, 0, s>>>(ops.p, k, gaps.p, scan.p, n_ops, max_rc, last_gap, n2 - n_list, n2, cols.p);
     ZKM_LAUNCHED();
     unsigned* d_bad = (unsigned*)(misc.p + 1);
     ZKM_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), s));

@@ -146,7 +146,8 @@ void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t
 
 void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     {
-    ProfScope ps("merkle_levels", s, 48.0 * (double)(t.num_leaves() - ((size_t)1 << t.cap_height)));
+    const double parents = (double)(t.num_leaves() - ((size_t)1 << t.cap_height));
+    ProfScope ps("merkle_levels", s, 96.0 * parents, parents);      // 64 B in + 32 B out, one permutation per parent
     for (int l = 1; l < t.num_levels(); l++) {
         size_t np = (size_t)1 << (t.log_leaves - l);
         if (np <= ((size_t)1 << 14)) {
@@ -167,14 +168,14 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
 void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s) {
     size_t N = (size_t)1 << (log_n + rate_bits);
     unsigned blocks = (unsigned)((N + 127) / 128);
-    ProfScope ps("leaf_hash", s, (double)N * (8.0 * ncols + 32.0));
+    ProfScope ps("leaf_hash", s, (double)N * (8.0 * ncols + 32.0), ncols > 4 ? (double)N * ((ncols + 7) / 8) : 0.0);
     lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests);
     ZKM_LAUNCHED();
 }
 
 void rows_leaf_hash(const u64* rows, int width, size_t num_leaves, u64* leaf_digests, cudaStream_t s) {
     unsigned blocks = (unsigned)((num_leaves + 127) / 128);
-    ProfScope ps("leaf_hash_rows", s, (double)num_leaves * (8.0 * width + 32.0));
+    ProfScope ps("leaf_hash_rows", s, (double)num_leaves * (8.0 * width + 32.0), width > 4 ? (double)num_leaves * ((width + 7) / 8) : 0.0);
     rows_leaf_hash_kernel<<<blocks, 128, 0, s>>>(rows, width, num_leaves, leaf_digests);
     ZKM_LAUNCHED();
 }

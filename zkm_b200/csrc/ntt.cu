@@ -196,15 +196,16 @@ static ntt_kernel_t kernel_for(int log_r) {
     throw std::runtime_error("unsupported NTT radix");
 }
 
-static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s) {
+static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s, double alg_bytes) {
     size_t R = (size_t)1 << log_r;
     p.log_T = 0;
     while ((1 << p.log_T) < p.T) p.log_T++;
     ZKM_CHECK((1 << p.log_T) == p.T, "NTT tile width must be a power of two");
     size_t smem = (R + R * (p.T + 1)) * sizeof(u64);
     ntt_kernel_t k = kernel_for(log_r);
-    // algorithmic bytes of one pass: every element read once and written once
-    ProfScope ps("ntt_pass", s, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
+    // alg_bytes: this launch's share of the transform's algorithmic bytes (inputs read once, outputs
+    // written once -- charged to the first pass); the second counter is the traffic of the pass itself, 16 B per element
+    ProfScope ps("ntt_pass", s, alg_bytes, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
     if (smem > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one radix-16 work item per thread per step when the tile is large enough (8 warps per SM sub-partition)
     size_t items = (R >> (log_r >= 4 ? 4 : log_r)) * (size_t)p.T;
@@ -239,6 +240,7 @@ static std::shared_ptr<PowTableOwner> get_roots(NttTables& T, int log_n, int inv
     T.impl->roots[key] = t;
     return t;
 }
+PowTable ntt_root_table(NttTables& t, int log_n, int inverse, cudaStream_t s) { return get_roots(t, log_n, inverse, s)->view; }
 static const u64* get_tw(NttTables& T, int log_r, int inverse, cudaStream_t s) {
     std::lock_guard<std::mutex> g(T.impl->mu);
     auto key = std::make_pair(log_r, inverse);
@@ -283,8 +285,10 @@ static void plan(int log_n, int& l1, int& l2, int& T) {
 }
 
 // One size-n transform per (column, z).  shifts: optional pre-scale tables per z (coset).
+// alg_bytes_per_col: algorithmic bytes of the whole call per column.
 static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_zs, u64* out, size_t out_cs, size_t out_zs,
-                        int ncols, int nz, int log_n, int inverse, const PowTable* pre, u64 final_scale, cudaStream_t s) {
+                        int ncols, int nz, int log_n, int inverse, const PowTable* pre, u64 final_scale, cudaStream_t s,
+                        double alg_bytes_per_col) {
     if (ncols == 0) return;
     int l1, l2, T;
     plan(log_n, l1, l2, T);
@@ -309,7 +313,7 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         p.has_post = 0; p.scale = final_scale;
         p.tw = get_tw(tabs, l1, inverse, s);
         dim3 grid((ncols + T - 1) / T, 1, nz);
-        launch_pass(l1, p, grid, s);
+        launch_pass(l1, p, grid, s, alg_bytes_per_col * ncols);
         return;
     }
     size_t n1 = (size_t)1 << l1, n2 = (size_t)1 << l2;
@@ -334,7 +338,7 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         p.post = roots->view; p.has_post = 1; p.post_b = T; p.post_t = 1;
         p.scale = 1;
         p.tw = twA;
-        launch_pass(l1, p, dim3((unsigned)(n2 / T), nc, nz), s);
+        launch_pass(l1, p, dim3((unsigned)(n2 / T), nc, nz), s, alg_bytes_per_col * nc);
         // pass B: scratch rows k1 (contiguous i2) -> out[k1 + n1*k2]
         NttPassParams q = {};
         for (int e = 0; e < 8; e++) q.w16[e] = p.w16[e];
@@ -345,16 +349,16 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         q.load_t_fast = 0; q.store_t_fast = 1;
         q.has_pre = 0; q.has_post = 0; q.scale = final_scale;
         q.tw = twB;
-        launch_pass(l2, q, dim3((unsigned)(n1 / T), nc, nz), s);
+        launch_pass(l2, q, dim3((unsigned)(n1 / T), nc, nz), s, 0.0);
     }
 }
 
 void ntt_forward(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s) {
-    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 0, nullptr, 1, s);
+    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 0, nullptr, 1, s, 16.0 * ((size_t)1 << log_n));
 }
 void ntt_inverse(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s) {
     gl ninv = gl_inv(gl((u64)1 << log_n));
-    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 1, nullptr, ninv.v, s);
+    ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 1, nullptr, ninv.v, s, 16.0 * ((size_t)1 << log_n));
 }
 void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t out_cs, int ncols, int log_n, int rate_bits,
                cudaStream_t s, int shift_exp_bits) {
@@ -363,7 +367,9 @@ void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t o
     PowTable pre[4];
     std::shared_ptr<PowTableOwner> keep[4];
     for (int j = 0; j < nz; j++) { keep[j] = get_shift(t, log_n, rate_bits, j, 0, s, shift_exp_bits); pre[j] = keep[j]->view; }
-    ntt_generic(t, coeffs, in_cs, 0, lde, out_cs, (size_t)1 << log_n, ncols, nz, log_n, 0, pre, 1, s);
+    // section 8(d): the LDE writes 8*n*nz bytes per column; its input is the coefficient vector the preceding iNTT (or fold)
+    // just wrote, which the survey's 48*n*C figure for iNTT + LDE does not count a second time
+    ntt_generic(t, coeffs, in_cs, 0, lde, out_cs, (size_t)1 << log_n, ncols, nz, log_n, 0, pre, 1, s, 8.0 * nz * ((size_t)1 << log_n));
 }
 
 // values on the coset 7*H_n (natural order) -> coefficients:  ifft then scale coefficient i by 7^-i.

@@ -14,6 +14,10 @@ struct NttTables {
     NttTables& operator=(const NttTables&) = delete;
 };
 
+// Cached two-level power table of w_{2^log_n} (or its inverse) for exponents < 2^log_n; lives as long as the tables.
+struct PowTable;
+PowTable ntt_root_table(NttTables& t, int log_n, int inverse, cudaStream_t s);
+
 // All buffers are column-major: column c starts at base + c*col_stride (elements); in == out allowed.
 // out[k] = sum_i in[i] w_n^(ik), natural order both sides.
 void ntt_forward(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out_cs, int ncols, int log_n, cudaStream_t s);

@@ -9,8 +9,8 @@
 namespace zkm {
 
 namespace {
-struct Pending { std::string name; cudaEvent_t e0, e1; double bytes; };
-struct Total { double ms = 0; unsigned long long launches = 0; double bytes = 0; };
+struct Pending { std::string name; cudaEvent_t e0, e1; double bytes, aux; };
+struct Total { double ms = 0; unsigned long long launches = 0; double bytes = 0, aux = 0; };
 bool g_on = false;
 std::mutex g_mu;                               // worker contexts may profile from several host threads
 std::vector<Pending> g_pending;
@@ -31,14 +31,14 @@ void resolve() {
         cudaEventElapsedTime(&ms, p.e0, p.e1);
         auto it = g_totals.find(p.name);
         if (it == g_totals.end()) { g_order.push_back(p.name); it = g_totals.emplace(p.name, Total()).first; }
-        it->second.ms += ms; it->second.launches++; it->second.bytes += p.bytes;
+        it->second.ms += ms; it->second.launches++; it->second.bytes += p.bytes; it->second.aux += p.aux;
         g_pool.push_back(p.e0); g_pool.push_back(p.e1);
     }
     g_pending.clear();
 }
 }  // namespace
 
-ProfScope::ProfScope(const char* name_, cudaStream_t s_, double b) : name(name_), s(s_), bytes(b) {
+ProfScope::ProfScope(const char* name_, cudaStream_t s_, double b, double aux_) : name(name_), s(s_), bytes(b), aux(aux_) {
     if (!g_on) return;
     std::lock_guard<std::mutex> lk(g_mu);
     e0 = get_event(); e1 = get_event();
@@ -48,12 +48,12 @@ ProfScope::~ProfScope() {
     if (!e0) return;
     std::lock_guard<std::mutex> lk(g_mu);
     cudaEventRecord(e1, s);
-    g_pending.push_back({name, e0, e1, bytes});
+    g_pending.push_back({name, e0, e1, bytes, aux});
     if (g_pending.size() > 8192) resolve();
 }
 void prof_enable(bool on) { g_on = on; }
 void prof_reset() { std::lock_guard<std::mutex> lk(g_mu); resolve(); g_totals.clear(); g_order.clear(); }
-bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes) {
+bool prof_get(const char* name, double* ms, unsigned long long* launches, double* bytes, double* aux) {
     std::lock_guard<std::mutex> lk(g_mu);
     resolve();
     auto it = g_totals.find(name);
@@ -61,6 +61,7 @@ bool prof_get(const char* name, double* ms, unsigned long long* launches, double
     if (ms) *ms = it->second.ms;
     if (launches) *launches = it->second.launches;
     if (bytes) *bytes = it->second.bytes;
+    if (aux) *aux = it->second.aux;
     return true;
 }
 std::string prof_names() {

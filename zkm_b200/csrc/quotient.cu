@@ -13,7 +13,6 @@
 #include "aux.cuh"
 #include "tables/registry.h"
 
-#include <mutex>
 
 namespace zkm {
 
@@ -28,13 +27,14 @@ constexpr int QUOTIENT_ALPHAS = 2;
 
 // The alpha-fold acc <- acc * alpha + c runs once per constraint (hundreds of times per point).  It is a
 // NON-inlined function so that its ~55 instructions exist once in the instruction cache instead of once per
-// constraint (the straight-line constraint code is instruction-fetch bound); the alphas live in constant memory.
-static __constant__ u64 c_quotient_alpha[QUOTIENT_ALPHAS];     // one copy per translation unit (see the bottom of the file)
+// constraint (the straight-line constraint code is instruction-fetch bound).  The alphas arrive as kernel parameters
+// (QParams::alphas, i.e. the kernel's own constant bank) and are handed to the fold by the consumer: no device-wide
+// state, so proofs on different worker contexts never serialise on it.
 struct FoldPair { u64 a0, a1; };
-static __device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c) {
+static __device__ __noinline__ FoldPair quotient_fold(u64 a0, u64 a1, u64 c, u64 alpha0, u64 alpha1) {
     FoldPair r;
-    r.a0 = (gl(a0) * gl(c_quotient_alpha[0]) + gl(c)).v;
-    r.a1 = (gl(a1) * gl(c_quotient_alpha[1]) + gl(c)).v;
+    r.a0 = (gl(a0) * gl(alpha0) + gl(c)).v;
+    r.a1 = (gl(a1) * gl(alpha1) + gl(c)).v;
     return r;
 }
 
@@ -52,7 +52,7 @@ struct DevConsumer {
     int worker = 0, workers = 1, px = 0, npx = 0;      // cooperative mode: this thread's worker id, point slot
     u64* stage = nullptr;                              // shared memory [COOP_CHUNK][npx]
     __device__ __forceinline__ void constraint(gl c) {
-        FoldPair r = quotient_fold(acc[0].v, acc[1].v, c.v);
+        FoldPair r = quotient_fold(acc[0].v, acc[1].v, c.v, alpha[0].v, alpha[1].v);
         acc[0] = gl(r.a0); acc[1] = gl(r.a1);
     }
     // Re-converges the CTA: the constraint code is straight-line and instruction-fetch bound (ncu: "no instruction"
@@ -179,8 +179,13 @@ __device__ __forceinline__ gl gl_inv_q(gl x) {
     return gl_exp2(x31, 33) * x32;
 }
 
+// Register budget: with __launch_bounds__(512) alone ptxas settles on 64 registers and spills ~500 B per thread in the CPU
+// table's kernel; (512, 1) gives it 128 registers (no spills) at half the resident warps.  ZKM_Q_MINBLOCKS selects (A/B builds).
+#ifndef ZKM_Q_MINBLOCKS
+#define ZKM_Q_MINBLOCKS 1
+#endif
 template <int KIND, bool COOP>
-__global__ void __launch_bounds__(512) quotient_kernel(QParams q) {
+__global__ void __launch_bounds__(512, ZKM_Q_MINBLOCKS) quotient_kernel(QParams q) {
     __shared__ u64 coop_stage[COOP ? COOP_CHUNK * COOP_PX : 1];
     const size_t n = (size_t)1 << q.log_n;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the 2n points exactly (no early exit: checkpoints)
@@ -223,14 +228,11 @@ typedef void (*quotient_kernel_t)(QParams);
 #define ZKM_QPART 0
 #endif
 #define ZKM_QK(k) case tables::k: kern = coop ? quotient_kernel<tables::k, true> : quotient_kernel<tables::k, false>; break;
-// Returns the kernel for `kind` if this translation unit holds it (after loading the alphas into this unit's own
-// constant-memory copy), else nullptr.
+// Returns the kernel for `kind` if this translation unit holds it, else nullptr.
 #define ZKM_QPART_FN(name, cases)                                                                          \
-    quotient_kernel_t name(int kind, bool coop, const u64* host_alphas, cudaStream_t s) {                  \
+    quotient_kernel_t name(int kind, bool coop) {                                                          \
         quotient_kernel_t kern = nullptr;                                                                  \
         switch (kind) { cases default: break; }                                                            \
-        if (kern) ZKM_CUDA(cudaMemcpyToSymbolAsync(c_quotient_alpha, host_alphas, sizeof(u64) * QUOTIENT_ALPHAS, 0, \
-                                                   cudaMemcpyHostToDevice, s));                           \
         return kern;                                                                                       \
     }
 #if ZKM_QPART == 0
@@ -245,14 +247,14 @@ ZKM_QPART_FN(quotient_kernels_part3, ZKM_QK(T_SHA_EXTEND) ZKM_QK(T_SHA_EXTEND_SP
 #undef ZKM_QK
 
 #if ZKM_QPART == 0
-quotient_kernel_t quotient_kernels_part1(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
-quotient_kernel_t quotient_kernels_part2(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
-quotient_kernel_t quotient_kernels_part3(int kind, bool coop, const u64* host_alphas, cudaStream_t s);
-static quotient_kernel_t quotient_kernel_for(int kind, bool coop, const u64* host_alphas, cudaStream_t s) {
-    quotient_kernel_t k = quotient_kernels_part0(kind, coop, host_alphas, s);
-    if (!k) k = quotient_kernels_part1(kind, coop, host_alphas, s);
-    if (!k) k = quotient_kernels_part2(kind, coop, host_alphas, s);
-    if (!k) k = quotient_kernels_part3(kind, coop, host_alphas, s);
+quotient_kernel_t quotient_kernels_part1(int kind, bool coop);
+quotient_kernel_t quotient_kernels_part2(int kind, bool coop);
+quotient_kernel_t quotient_kernels_part3(int kind, bool coop);
+static quotient_kernel_t quotient_kernel_for(int kind, bool coop) {
+    quotient_kernel_t k = quotient_kernels_part0(kind, coop);
+    if (!k) k = quotient_kernels_part1(kind, coop);
+    if (!k) k = quotient_kernels_part2(kind, coop);
+    if (!k) k = quotient_kernels_part3(kind, coop);
     if (!k) throw std::runtime_error(std::string("constraints of table ") + tables::table_name(kind) + " are not available on the device");
     return k;
 }
@@ -271,8 +273,7 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     for (int a = 0; a < num_alphas; a++) q.alphas[a] = alphas[a];
     q.ch = ch;
     q.prog = prog.view;
-    auto tab = make_pow_table(gl_root_of_unity(log_n + 1), log_n + 1, s);
-    q.w2n = tab->view;
+    q.w2n = ntt_root_table(ctx().ntt, log_n + 1, 0, s);      // cached per context
     gl gn = gl_exp2(gl(GL_GENERATOR), log_n);                 // 7^n
     gl z0 = gn - gl::one(), z1 = -gn - gl::one();              // x^n = 7^n * (-1)^i
     q.zh[0] = z0.v; q.zh[1] = z1.v;
@@ -280,16 +281,9 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     gl g = gl_root_of_unity(log_n);
     q.g = g.v; q.last = gl_inv(g).v; q.n_inv = gl_inv(gl((u64)n)).v;
     q.q = d_q;
-    u64 ha[QUOTIENT_ALPHAS] = {0, 0};
-    for (int a = 0; a < num_alphas; a++) ha[a] = alphas[a];
     // cooperative variant while the 2n points cannot fill the machine: 32 points x 16 workers per CTA
     const bool coop = 2 * n <= 8192;
-    // c_quotient_alpha is one constant-memory slot per device: with several worker contexts the upload + kernel of one proof
-    // must not interleave with another's (the launch below is followed by a stream synchronisation, so holding the lock until
-    // the end of this function is enough)
-    static std::mutex quotient_mu;
-    std::lock_guard<std::mutex> quotient_lock(quotient_mu);
-    quotient_kernel_t k = quotient_kernel_for(kind, coop, ha, s);
+    quotient_kernel_t k = quotient_kernel_for(kind, coop);
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
     if (coop) {
         const unsigned px = 2 * n >= (size_t)COOP_PX ? COOP_PX : (unsigned)(2 * n);
@@ -299,7 +293,6 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
         k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
     }
     ZKM_LAUNCHED();
-    ZKM_CUDA(cudaStreamSynchronize(s));                      // keeps `tab` alive until the kernel has run
 }
 
 #endif  // ZKM_QPART == 0

@@ -9,8 +9,8 @@ namespace zkm {
 
 __global__ void transpose_rows_kernel(const u64* __restrict__ rows, u64* __restrict__ cols, size_t n, int ncols) {
     __shared__ u64 tile[32][33];
-    const size_t r0 = (size_t)blockIdx.y * 32;
-    const int c0 = blockIdx.x * 32;
+    const size_t r0 = (size_t)blockIdx.x * 32;          // row tiles on grid.x (up to 2^31 - 1), column tiles on grid.y (<= 65535)
+    const int c0 = blockIdx.y * 32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         const int c = c0 + threadIdx.x;
         if (c < ncols) tile[k][threadIdx.x] = rows[(r0 + k) * (size_t)ncols + c];
@@ -26,7 +26,8 @@ __global__ void transpose_rows_kernel(const u64* __restrict__ rows, u64* __restr
 void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cudaStream_t s) {
     ZKM_CHECK(n >= 32 && (n & (n - 1)) == 0, "transpose: height must be a power of two >= 32");
     ProfScope ps("transpose_rows", s, 16.0 * (double)n * ncols);
-    dim3 grid((unsigned)((ncols + 31) / 32), (unsigned)(n / 32));
+    ZKM_CHECK(n / 32 <= 0x7fffffffu && (ncols + 31) / 32 <= 65535, "transpose: table too large");
+    dim3 grid((unsigned)(n / 32), (unsigned)((ncols + 31) / 32));
     transpose_rows_kernel<<<grid, dim3(32, 8), 0, s>>>(rows, cols, n, ncols);
     ZKM_LAUNCHED();
 }

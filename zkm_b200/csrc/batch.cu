@@ -1,4 +1,5 @@
 #include "batch.cuh"
+#include "shard.cuh"
 #include <memory>
 #include <map>
 #include <mutex>
@@ -168,15 +169,31 @@ void ctx_shutdown() {
     cudaStreamDestroy(s);
 }
 
+// In-segment sharding applies to commitments big enough to pay for one 512-byte all-gather (tables below 2^13 rows are
+// latency bound on one GPU already -- they also take the cooperative small-table quotient kernel -- and are committed in
+// full by every rank).  The rule depends on the shape only, so every
+// rank takes the same branch.
+static bool commit_is_sharded(const Batch& b) {
+    return shard().active() && b.rate_bits == 2 && b.cap_height >= 2 && b.log_n >= 13;
+}
+static void commit_tree(Batch& b, cudaStream_t s) {
+    const Shard& sh = shard();
+    merkle_alloc(b.tree, b.lde_bits(), b.cap_height, s);
+    b.tree.sharded = b.sharded;
+    if (b.sharded) lde_leaf_hash(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s, sh.coset_begin(), sh.coset_count());
+    else lde_leaf_hash(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s);
+    merkle_build_from_leaf_digests(b.tree, s);
+}
 static void commit_lde(Batch& b) {
     Ctx& c = ctx();
     cudaStream_t s = c.stream;
+    const Shard& sh = shard();
     size_t N = b.lde_n();
+    b.sharded = commit_is_sharded(b);
     b.lde.alloc((size_t)b.ncols * N, s);
-    lde_coset(c.ntt, b.coeffs.p, b.n(), b.lde.p, N, b.ncols, b.log_n, b.rate_bits, s);
-    merkle_alloc(b.tree, b.lde_bits(), b.cap_height, s);
-    lde_leaf_hash(b.lde.p, N, b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s);
-    merkle_build_from_leaf_digests(b.tree, s);
+    if (b.sharded) lde_coset(c.ntt, b.coeffs.p, b.n(), b.lde.p, N, b.ncols, b.log_n, b.rate_bits, s, 0, sh.coset_begin(), sh.coset_count());
+    else lde_coset(c.ntt, b.coeffs.p, b.n(), b.lde.p, N, b.ncols, b.log_n, b.rate_bits, s);
+    commit_tree(b, s);
 }
 
 void batch_from_coeffs_dev(Batch& b, DevBuf&& coeffs, int ncols, int log_n, int rate_bits, int cap_height) {
@@ -198,6 +215,7 @@ void batch_from_values_grouped_dev(Batch& b, const u64* values, DevBuf&& coeffs,
     b.ncols = ncols; b.log_n = log_n; b.rate_bits = rate_bits; b.cap_height = cap_height;
     b.coeffs = std::move(coeffs);
     size_t n = b.n(), N = b.lde_n();
+    b.sharded = commit_is_sharded(b);
     b.lde.alloc((size_t)ncols * N, s);
     int c0 = 0;
     for (size_t k = 0; k < col_ends.size(); k++) {
@@ -205,12 +223,12 @@ void batch_from_values_grouped_dev(Batch& b, const u64* values, DevBuf&& coeffs,
         ZKM_CHECK(c1 > c0, "bad column groups");
         wait_group(k);
         ntt_inverse(c.ntt, values + (size_t)c0 * n, n, b.coeffs.p + (size_t)c0 * n, n, c1 - c0, log_n, s);
-        lde_coset(c.ntt, b.coeffs.p + (size_t)c0 * n, n, b.lde.p + (size_t)c0 * N, N, c1 - c0, log_n, rate_bits, s);
+        if (b.sharded) lde_coset(c.ntt, b.coeffs.p + (size_t)c0 * n, n, b.lde.p + (size_t)c0 * N, N, c1 - c0, log_n, rate_bits, s, 0,
+                                 shard().coset_begin(), shard().coset_count());
+        else lde_coset(c.ntt, b.coeffs.p + (size_t)c0 * n, n, b.lde.p + (size_t)c0 * N, N, c1 - c0, log_n, rate_bits, s);
         c0 = c1;
     }
-    merkle_alloc(b.tree, b.lde_bits(), cap_height, s);
-    lde_leaf_hash(b.lde.p, N, ncols, log_n, rate_bits, b.tree.digests.p, s);
-    merkle_build_from_leaf_digests(b.tree, s);
+    commit_tree(b, s);
 }
 
 void batch_from_values_dev(Batch& b, DevBuf&& values, int ncols, int log_n, int rate_bits, int cap_height) {

@@ -33,6 +33,7 @@ struct Batch {
     DevBuf coeffs;             // ncols x n            (column-major, natural order)
     DevBuf lde;                // ncols x (n<<rate)    (column-major, coset-major rows)
     MerkleTreeDev tree;
+    bool sharded = false;      // in-segment sharding (shard.cuh): only this rank's cosets of `lde` / quarters of `tree` exist here
     size_t n() const { return (size_t)1 << log_n; }
     size_t lde_n() const { return (size_t)1 << (log_n + rate_bits); }
     int lde_bits() const { return log_n + rate_bits; }

@@ -5,6 +5,7 @@
 #include "poseidon_v2.cuh"
 #include "poseidon_host.h"
 #include "prover.cuh"
+#include "shard.cuh"
 #include "tables/systems.h"
 #include <cstring>
 #include <cstdlib>
@@ -72,6 +73,23 @@ int zkm_b200_worker_bind(zkm_worker_t* w, char** err) {
 }
 void zkm_b200_worker_destroy(zkm_worker_t* w) {
     try { worker_destroy((Ctx*)w); } catch (...) {}
+}
+
+int zkm_b200_shard_unique_id(uint8_t out[128], char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(out, "null argument");
+    shard_unique_id(out);
+    ZKM_API_END
+}
+int zkm_b200_shard_init(int rank, int world, const uint8_t id[128], char** err) {
+    ZKM_API_BEGIN
+    shard_init(rank, world, id);
+    ZKM_API_END
+}
+int zkm_b200_shard_shutdown(char** err) {
+    ZKM_API_BEGIN
+    shard_shutdown();
+    ZKM_API_END
 }
 
 static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;

@@ -9,6 +9,8 @@
 // across the warp for every column); the row-major leaf matrix of the reference is never built.
 #include "merkle.cuh"
 #include "poseidon_v2.cuh"
+#include "shard.cuh"
+#include <cstring>
 
 namespace zkm {
 
@@ -19,10 +21,9 @@ __device__ __forceinline__ size_t lde_pos_of_leaf(u32 leaf, int log_n, int rate_
 }
 
 __global__ void __launch_bounds__(128, 8) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
-                                                            int rate_bits, u64* __restrict__ dig) {
-    const size_t N = (size_t)1 << (log_n + rate_bits);
-    size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= N) return;
+                                                            int rate_bits, u64* __restrict__ dig, size_t pos_begin, size_t pos_end) {
+    size_t pos = pos_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= pos_end) return;
     // position -> natural index -> leaf index
     u32 j = (u32)(pos >> log_n), i = (u32)(pos & (((size_t)1 << log_n) - 1));
     u32 m = (i << rate_bits) | j;
@@ -73,9 +74,18 @@ __global__ void __launch_bounds__(128, 8) rows_leaf_hash_kernel(const u64* __res
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-__global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+// Which quarters of a level this launch covers (in-segment sharding, shard.cuh: a rank builds only the subtrees over the
+// leaf quarters it owns).  Thread i works on node q[i >> log_qsize] * qsize + (i & (qsize - 1)); the identity map
+// {4, {0,1,2,3}} is the whole level.
+struct QuarterMap { int nq; int q[4]; int log_qsize; };
+__device__ __forceinline__ size_t quarter_node(const QuarterMap& m, size_t i) {
+    return ((size_t)m.q[i >> m.log_qsize] << m.log_qsize) | (i & (((size_t)1 << m.log_qsize) - 1));
+}
+__global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents,
+                                                           QuarterMap qm) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parents) return;
+    i = quarter_node(qm, i);
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + i * 8);
     ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
     u64 s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
@@ -90,10 +100,12 @@ __global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restr
 // share one permutation, one state word each: the S-boxes of a full round run side by side and the MDS row of a lane is
 // 12 shuffled multiply-adds, so the dependent instruction chain is ~4x shorter.  Two permutations per warp (lanes 0-11
 // and 16-27).  Same merged partial-round constants as poseidon_permute_v8; outputs are bit-identical.
-__global__ void __launch_bounds__(128) merkle_level_coop_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents) {
+__global__ void __launch_bounds__(128) merkle_level_coop_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents,
+                                                             QuarterMap qm) {
     const unsigned lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
-    const size_t node = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * 2 + grp;
-    const bool live = sub < 12 && node < n_parents;
+    const size_t slot = ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * 2 + grp;
+    const bool live = sub < 12 && slot < n_parents;
+    const size_t node = slot < n_parents ? quarter_node(qm, slot) : 0;
     const unsigned base = grp << 4;                      // first lane of this permutation's group
     u64 s = (live && sub < 8) ? child[node * 8 + sub] : 0;
     const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -145,31 +157,62 @@ void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t
 }
 
 void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
+    const Shard& sh = shard();
+    const bool sharded = t.sharded && sh.active();
+    ZKM_CHECK(!sharded || t.cap_height >= 2, "sharded trees need cap_height >= 2 (whole cap subtrees per leaf quarter)");
+    QuarterMap qm = {4, {0, 1, 2, 3}, 0};
+    if (sharded) {
+        qm.nq = sh.coset_count();
+        for (int k = 0; k < qm.nq; k++) qm.q[k] = bitrev2(sh.coset_begin() + k);      // coset j = leaf quarter bitrev2(j)
+    }
     {
-    const double parents = (double)(t.num_leaves() - ((size_t)1 << t.cap_height));
+    const double parents = (double)(t.num_leaves() - ((size_t)1 << t.cap_height)) * qm.nq / 4;
     ProfScope ps("merkle_levels", s, 96.0 * parents, parents);      // 64 B in + 32 B out, one permutation per parent
     for (int l = 1; l < t.num_levels(); l++) {
-        size_t np = (size_t)1 << (t.log_leaves - l);
+        const int log_np = t.log_leaves - l;
+        qm.log_qsize = log_np - 2;
+        size_t np = ((size_t)1 << qm.log_qsize) * qm.nq;             // parents this rank computes on this level
         if (np <= ((size_t)1 << 14)) {
-            merkle_level_coop_kernel<<<(unsigned)((np + 7) / 8), 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+            merkle_level_coop_kernel<<<(unsigned)((np + 7) / 8), 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np, qm);
         } else {
             unsigned blocks = (unsigned)((np + 127) / 128);
-            merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np);
+            merkle_level_kernel<<<blocks, 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np, qm);
         }
         ZKM_LAUNCHED();
     }
     }
-    size_t ncap = (size_t)4 << t.cap_height;
+    const size_t ncap = (size_t)4 << t.cap_height;          // words
     t.cap.resize(ncap);
-    ZKM_CUDA(cudaMemcpyAsync(t.cap.data(), t.digests.p + t.level_off.back(), ncap * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    ZKM_CUDA(cudaStreamSynchronize(s));
+    if (!sharded) {
+        ZKM_CUDA(cudaMemcpyAsync(t.cap.data(), t.digests.p + t.level_off.back(), ncap * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        ZKM_CUDA(cudaStreamSynchronize(s));
+        return;
+    }
+    // the only exchange of a sharded commitment: every rank contributes the cap entries of its leaf quarters (ncclAllGather,
+    // 512 B per tree in total); afterwards all ranks hold the same cap and run the same transcript
+    const size_t qwords = ncap / 4, mine = qwords * qm.nq;
+    DevBuf send(mine, s), recv(mine * sh.world, s);
+    for (int k = 0; k < qm.nq; k++)
+        ZKM_CUDA(cudaMemcpyAsync(send.p + k * qwords, t.digests.p + t.level_off.back() + (size_t)qm.q[k] * qwords, qwords * sizeof(u64),
+                                 cudaMemcpyDeviceToDevice, s));
+    shard_all_gather(send.p, recv.p, mine, s);
+    std::vector<u64> all(mine * sh.world);
+    recv.download(all.data(), all.size());
+    for (int r = 0; r < sh.world; r++)
+        for (int k = 0; k < qm.nq; k++) {
+            const int q = bitrev2(r * qm.nq + k);
+            memcpy(t.cap.data() + (size_t)q * qwords, all.data() + ((size_t)r * qm.nq + k) * qwords, qwords * sizeof(u64));
+        }
 }
 
-void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s) {
-    size_t N = (size_t)1 << (log_n + rate_bits);
+void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s,
+                   int coset_begin, int coset_count) {
+    if (coset_count < 0) coset_count = (1 << rate_bits) - coset_begin;
+    const size_t pos_begin = (size_t)coset_begin << log_n, pos_end = (size_t)(coset_begin + coset_count) << log_n;
+    size_t N = pos_end - pos_begin;                          // leaves hashed by this call
     unsigned blocks = (unsigned)((N + 127) / 128);
     ProfScope ps("leaf_hash", s, (double)N * (8.0 * ncols + 32.0), ncols > 4 ? (double)N * ((ncols + 7) / 8) : 0.0);
-    lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests);
+    lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests, pos_begin, pos_end);
     ZKM_LAUNCHED();
 }
 

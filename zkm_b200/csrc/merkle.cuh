@@ -13,6 +13,9 @@ struct MerkleTreeDev {
     DevBuf digests;
     std::vector<size_t> level_off;          // element (u64) offset of each level
     std::vector<u64> cap;                   // host copy: (1<<cap_height)*4 words
+    // in-segment sharding (shard.cuh): this rank fills and builds only the leaf quarters of the cosets it owns; the cap is
+    // completed by an all-gather.  Digests of the other quarters are never written or read on this rank.
+    bool sharded = false;
     int num_levels() const { return log_leaves - cap_height + 1; }
     size_t num_leaves() const { return (size_t)1 << log_leaves; }
 };
@@ -23,7 +26,9 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s);
 
 // Leaf digests of a coset-major LDE (ntt.cuh lde_coset): leaf index = bitrev(natural LDE index).
 // ncols <= 4: the row itself, zero padded (plonky2 hash_or_noop); else overwrite-mode sponge.
-void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s);
+// [coset_begin, coset_begin + coset_count): hash only the leaves of those cosets (coset_count < 0: all remaining).
+void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s,
+                   int coset_begin = 0, int coset_count = -1);
 
 // Leaf digests for rows stored row-major and already in leaf order: rows[leaf*width .. +width).
 void rows_leaf_hash(const u64* rows, int width, size_t num_leaves, u64* leaf_digests, cudaStream_t s);

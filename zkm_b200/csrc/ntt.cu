@@ -361,15 +361,19 @@ void ntt_inverse(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out
     ntt_generic(t, in, in_cs, 0, out, out_cs, 0, ncols, 1, log_n, 1, nullptr, ninv.v, s, 16.0 * ((size_t)1 << log_n));
 }
 void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t out_cs, int ncols, int log_n, int rate_bits,
-               cudaStream_t s, int shift_exp_bits) {
+               cudaStream_t s, int shift_exp_bits, int coset_begin, int coset_count) {
     ZKM_CHECK(rate_bits <= 2, "rate_bits > 2 unsupported");
-    int nz = 1 << rate_bits;
+    const int all = 1 << rate_bits;
+    if (coset_count < 0) coset_count = all - coset_begin;
+    ZKM_CHECK(coset_begin >= 0 && coset_count >= 1 && coset_begin + coset_count <= all, "bad coset range");
+    const int nz = coset_count;
+    const size_t n = (size_t)1 << log_n;
     PowTable pre[4];
     std::shared_ptr<PowTableOwner> keep[4];
-    for (int j = 0; j < nz; j++) { keep[j] = get_shift(t, log_n, rate_bits, j, 0, s, shift_exp_bits); pre[j] = keep[j]->view; }
-    // section 8(d): the LDE writes 8*n*nz bytes per column; its input is the coefficient vector the preceding iNTT (or fold)
-    // just wrote, which the survey's 48*n*C figure for iNTT + LDE does not count a second time
-    ntt_generic(t, coeffs, in_cs, 0, lde, out_cs, (size_t)1 << log_n, ncols, nz, log_n, 0, pre, 1, s, 8.0 * nz * ((size_t)1 << log_n));
+    for (int z = 0; z < nz; z++) { keep[z] = get_shift(t, log_n, rate_bits, coset_begin + z, 0, s, shift_exp_bits); pre[z] = keep[z]->view; }
+    // section 8(d): the LDE writes 8*n bytes per coset and column; its input is the coefficient vector the preceding iNTT (or
+    // fold) just wrote, which the survey's 48*n*C figure for iNTT + LDE does not count a second time
+    ntt_generic(t, coeffs, in_cs, 0, lde + (size_t)coset_begin * n, out_cs, n, ncols, nz, log_n, 0, pre, 1, s, 8.0 * nz * n);
 }
 
 // values on the coset 7*H_n (natural order) -> coefficients:  ifft then scale coefficient i by 7^-i.

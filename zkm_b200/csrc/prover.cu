@@ -5,6 +5,7 @@
 // the proof buffer (layout: include/zkm_b200.h "Proof buffer layout").
 #include "prover.cuh"
 #include "fri.cuh"
+#include "shard.cuh"
 #include "poseidon.cuh"
 #include "poseidon_host.h"
 #include "tables/systems.h"
@@ -269,13 +270,33 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     const int plen = log_n + cfg.rate_bits - cfg.cap_height;
     for (int o = 0; o < 3; o++) {
         const Batch& b = *oracles[o];
-        DevBuf rows((size_t)nq * b.ncols, s), paths((size_t)nq * plen * 4 + 1, s);
+        const size_t nrow = (size_t)nq * b.ncols, npath = (size_t)nq * plen * 4;
+        o_rows[o].resize(nrow);
+        o_paths[o].resize(npath);
+        if (b.sharded) {
+            // in-segment sharding: a queried leaf and its authentication path live on the rank that owns its coset; every
+            // rank answers all queries from what it holds, the answers are all-gathered and the owner's copy is kept
+            const Shard& sh = shard();
+            const size_t per = nrow + npath;
+            DevBuf pack(per, s), all(per * sh.world, s);
+            lde_gather_rows(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, (const u32*)didx.p, nq, pack.p, s);
+            merkle_gather_paths(b.tree, (const u32*)didx.p, nq, pack.p + nrow, s);
+            shard_all_gather(pack.p, all.p, per, s);
+            std::vector<u64> h(per * sh.world);
+            all.download(h.data(), h.size());
+            for (int q = 0; q < nq; q++) {
+                const int quarter = (int)(qidx[q] >> (b.lde_bits() - 2));
+                const u64* src = h.data() + (size_t)Shard::coset_owner(bitrev2(quarter), sh.world) * per;
+                memcpy(o_rows[o].data() + (size_t)q * b.ncols, src + (size_t)q * b.ncols, (size_t)b.ncols * sizeof(u64));
+                memcpy(o_paths[o].data() + (size_t)q * plen * 4, src + nrow + (size_t)q * plen * 4, (size_t)plen * 4 * sizeof(u64));
+            }
+            continue;
+        }
+        DevBuf rows(nrow, s), paths(npath + 1, s);
         lde_gather_rows(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, (const u32*)didx.p, nq, rows.p, s);
         merkle_gather_paths(b.tree, (const u32*)didx.p, nq, paths.p, s);
-        o_rows[o].resize((size_t)nq * b.ncols);
-        rows.download(o_rows[o].data(), o_rows[o].size());
-        o_paths[o].resize((size_t)nq * plen * 4);
-        if (plen) paths.download(o_paths[o].data(), o_paths[o].size());
+        rows.download(o_rows[o].data(), nrow);
+        if (plen) paths.download(o_paths[o].data(), npath);
     }
     std::vector<std::vector<u64>> s_rows(rounds.size()), s_paths(rounds.size());
     std::vector<int> s_plen(rounds.size());

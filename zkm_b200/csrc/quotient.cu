@@ -11,6 +11,7 @@
 // fully coalesced 8-byte-per-lane access and the next-row read hits the neighbouring lane's line.
 // Only half of the LDE (2 of 4 cosets) is read: 16*n*(C+A) algorithmic bytes.
 #include "aux.cuh"
+#include "shard.cuh"
 #include "tables/registry.h"
 
 
@@ -74,6 +75,9 @@ struct QParams {
     u64 zh[2], zh_inv[2];         // Z_H(x_i) for i even / odd, and inverses
     u64 last, g, n_inv;           // g^(n-1) = g^-1, g = w_n, 1/n
     u64* q;
+    // in-segment sharding: the launch covers one half of the quotient domain (coset 0 or coset 2 of the LDE) and writes it
+    // half-major, q[(half * na + a) * n + idx], for the exchange; otherwise both halves, natural order q[a * 2n + 2 idx + half]
+    int half_base, half_major;
 };
 
 // Column::eval (no next-row terms), used by the logUp Z check (lookup.rs:182-187).
@@ -179,16 +183,21 @@ __device__ __forceinline__ gl gl_inv_q(gl x) {
     return gl_exp2(x31, 33) * x32;
 }
 
-// Register budget: with __launch_bounds__(512) alone ptxas settles on 64 registers and spills ~500 B per thread in the CPU
-// table's kernel; (512, 1) gives it 128 registers (no spills) at half the resident warps.  ZKM_Q_MINBLOCKS selects (A/B builds).
+// Register budget, measured on U20 (profiles/r2a_quotient_regs.txt): 64 registers (2 CTAs of 512 threads per SM, ~500 B of
+// spills per thread in the CPU table's kernel) 27.4 ms per proof; 128 registers (no spills, half the resident warps) 33.9 ms:
+// the kernel is latency/issue bound and wants the warps more than the registers.  ZKM_Q_THREADS / ZKM_Q_MINBLOCKS for A/B builds.
+#ifndef ZKM_Q_THREADS
+#define ZKM_Q_THREADS 512
+#endif
 #ifndef ZKM_Q_MINBLOCKS
-#define ZKM_Q_MINBLOCKS 1
+#define ZKM_Q_MINBLOCKS 2
 #endif
 template <int KIND, bool COOP>
-__global__ void __launch_bounds__(512, ZKM_Q_MINBLOCKS) quotient_kernel(QParams q) {
+__global__ void __launch_bounds__(COOP ? 512 : ZKM_Q_THREADS, COOP ? 1 : ZKM_Q_MINBLOCKS) quotient_kernel(QParams q) {
     __shared__ u64 coop_stage[COOP ? COOP_CHUNK * COOP_PX : 1];
     const size_t n = (size_t)1 << q.log_n;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the 2n points exactly (no early exit: checkpoints)
+    // the grid covers the 2n points (or, sharded, the n points of one half) exactly: no early exit (checkpoints)
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + ((size_t)q.half_base << q.log_n);
     const size_t half = t >> q.log_n, idx = t & (n - 1);
     const size_t i = 2 * idx + half;                        // index in the quotient domain 7*H_{2n}
     const size_t pos = (2 * half) * n + idx, pos_next = (2 * half) * n + ((idx + 1) & (n - 1));
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(512, ZKM_Q_MINBLOCKS) quotient_kernel(QParams 
     gl zi(q.zh_inv[i & 1]);
 #pragma unroll
     for (int a = 0; a < QUOTIENT_ALPHAS; a++)
-        if (a < q.na) q.q[(size_t)a * 2 * n + i] = (yc.acc[a] * zi).v;
+        if (a < q.na) q.q[q.half_major ? (half * q.na + a) * n + idx : (size_t)a * 2 * n + i] = (yc.acc[a] * zi).v;
 }
 
 // The 12 x 2 kernel instantiations are spread over four translation units (quotient.cu = part 0 plus the launcher,
@@ -259,6 +268,15 @@ static quotient_kernel_t quotient_kernel_for(int kind, bool coop) {
     return k;
 }
 
+// half-major quotient values (sharded evaluation) -> natural order: q[a * 2n + 2 idx + half] = halves[(half * na + a) * n + idx]
+__global__ void quotient_interleave_kernel(const u64* __restrict__ halves, u64* __restrict__ q, int log_n, int na) {
+    const size_t n = (size_t)1 << log_n;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n * na) return;
+    const size_t a = t / (2 * n), i = t - a * 2 * n;
+    q[t] = halves[((i & 1) * na + a) * n + (i >> 1)];
+}
+
 void compute_quotient_values(int kind, const DProgram& prog, const tables::TableLayout& L, const Batch& trace, const Batch& aux,
                              const AuxChallenges& ch, const u64* alphas, int num_alphas, u64* d_q, cudaStream_t s) {
     ZKM_CHECK(num_alphas >= 1 && num_alphas <= QUOTIENT_ALPHAS, "num_challenges above 2 is not supported by the quotient kernels");
@@ -284,12 +302,32 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
     // cooperative variant while the 2n points cannot fill the machine: 32 points x 16 workers per CTA
     const bool coop = 2 * n <= 8192;
     quotient_kernel_t k = quotient_kernel_for(kind, coop);
+    const Shard& sh = shard();
+    if (trace.sharded) {
+        // each half of the quotient domain is evaluated by the rank that owns its coset (half h = LDE coset 2h), then both
+        // halves are broadcast so that every rank continues with the complete quotient values (shard.cuh)
+        ZKM_CHECK(aux.sharded && !coop && sh.active(), "quotient: inconsistent sharding");
+        DevBuf halves((size_t)2 * num_alphas * n, s);
+        q.q = halves.p; q.half_major = 1;
+        for (int h = 0; h < 2; h++) {
+            if (!sh.owns_coset(2 * h)) continue;
+            q.half_base = h;
+            ProfScope ps("quotient", s, 8.0 * (double)n * (L.ncols + L.num_aux()) + 8.0 * (double)n * num_alphas);
+            k<<<(unsigned)(n / ZKM_Q_THREADS), ZKM_Q_THREADS, 0, s>>>(q);
+            ZKM_LAUNCHED();
+        }
+        for (int h = 0; h < 2; h++)
+            shard_broadcast(halves.p + (size_t)h * num_alphas * n, (size_t)num_alphas * n, Shard::coset_owner(2 * h, sh.world), s);
+        quotient_interleave_kernel<<<(unsigned)((2 * n * num_alphas + 255) / 256), 256, 0, s>>>(halves.p, d_q, log_n, num_alphas);
+        ZKM_LAUNCHED();
+        return;
+    }
     ProfScope ps("quotient", s, 16.0 * (double)n * (L.ncols + L.num_aux()) + 16.0 * (double)n * num_alphas);
     if (coop) {
         const unsigned px = 2 * n >= (size_t)COOP_PX ? COOP_PX : (unsigned)(2 * n);
         k<<<(unsigned)(2 * n / px), dim3(px, 16), 0, s>>>(q);
     } else {
-        const unsigned threads = 512;
+        const unsigned threads = ZKM_Q_THREADS;
         k<<<(unsigned)(2 * n / threads), threads, 0, s>>>(q);
     }
     ZKM_LAUNCHED();

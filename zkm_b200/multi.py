@@ -69,3 +69,87 @@ def prove_segments(prove: Callable[[int], np.ndarray], num_segments: int, rank: 
     ids = shard_segments(num_segments, rank, world_size)
     local = [prove(i) for i in ids]
     return gather_proofs(local, ids, num_segments, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# In-segment sharding (include/zkm_b200.h "In-segment sharding"): G = 2 or 4 ranks prove ONE segment together.
+# The ownership rules below are the host-side mirror of zkm_b200/csrc/shard.cuh, used to form the groups and -- in the CPU
+# tests (gloo, the oracle as each rank's local prover) -- to check that the exchanged pieces reassemble the single-rank result.
+
+def bitrev(x: int, bits: int) -> int:
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (x & 1)
+        x >>= 1
+    return r
+
+
+def owned_cosets(rank: int, group: int) -> List[int]:
+    """LDE cosets j (natural LDE index m = 4 i + j) owned by `rank` of a `group`-rank shard group: 4/group consecutive ones."""
+    if group not in (1, 2, 4):
+        raise ValueError("in-segment sharding supports groups of 1, 2 or 4 ranks")
+    per = 4 // group
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def coset_owner(j: int, group: int) -> int:
+    return j * group // 4
+
+
+def leaf_owner(leaf: int, log_leaves: int, group: int) -> int:
+    """Rank holding leaf `leaf` (bit-reversed LDE order) and its path: the top two leaf bits are the bit-reversed coset id."""
+    return coset_owner(bitrev(leaf >> (log_leaves - 2), 2), group)
+
+
+def owned_cap_entries(rank: int, group: int, cap_height: int = 4) -> List[int]:
+    """Cap entries (subtree roots over contiguous leaf blocks) a rank computes: those of its cosets' leaf quarters."""
+    per_quarter = (1 << cap_height) // 4
+    out = []
+    for j in owned_cosets(rank, group):
+        q = bitrev(j, 2)
+        out.extend(range(q * per_quarter, (q + 1) * per_quarter))
+    return out
+
+
+def assemble_cap(pieces: Sequence[np.ndarray], group: int, cap_height: int = 4) -> np.ndarray:
+    """The all-gather of a sharded commitment: pieces[r] = rank r's owned cap entries (in owned_cap_entries order, 4 words
+    each) -> the full cap."""
+    cap = np.zeros(((1 << cap_height), 4), dtype=np.uint64)
+    for r, piece in enumerate(pieces):
+        ids = owned_cap_entries(r, group, cap_height)
+        cap[ids] = np.asarray(piece, dtype=np.uint64).reshape(len(ids), 4)
+    return cap
+
+
+def shard_group_init(lib, group: int = 0):
+    """Forms in-segment shard groups of `group` consecutive ranks (default: min(world, 4)) out of the torch.distributed world
+    and binds this process's library context to its group: rank 0 of each group creates the NCCL unique id
+    (zkm_b200_shard_unique_id) and it reaches the other members through a torch.distributed broadcast.  Returns
+    (group_index, rank_in_group, group_size).  Collective over the whole world."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import lib as zl
+    world, rank = dist.get_world_size(), dist.get_rank()
+    g = group or min(world, 4)
+    if world % g or g not in (1, 2, 4):
+        raise ValueError(f"cannot split {world} ranks into shard groups of {g}")
+    gi, ri = rank // g, rank % g
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    ids = torch.zeros((world // g, 128), dtype=torch.uint8, device=dev)
+    if ri == 0 and g > 1:
+        buf = C.create_string_buffer(128)
+        err = C.c_void_p()
+        zl.check(lib, lib.zkm_b200_shard_unique_id(buf, C.byref(err)), err)
+        ids[gi] = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+    dist.all_reduce(ids, op=dist.ReduceOp.SUM)          # every row is written by exactly one rank
+    err = C.c_void_p()
+    zl.check(lib, lib.zkm_b200_shard_init(ri, g, bytes(ids[gi].cpu().numpy().tobytes()), C.byref(err)), err)
+    return gi, ri, g
+
+
+def shard_group_shutdown(lib):
+    import ctypes as C
+    from . import lib as zl
+    err = C.c_void_p()
+    zl.check(lib, lib.zkm_b200_shard_shutdown(C.byref(err)), err)

@@ -153,6 +153,13 @@ class Segment:
                                               C.byref(self.cfg), C.byref(out), C.byref(words), C.byref(err))
         self._finish(rc, err, out, words)
 
+    def step_device_keep(self):
+        lib = self.lib
+        out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+        rc = lib.zkm_b200_prove_system_device(self.SYSTEM_ALL_STARK, self.shapes, self.dptrs, 12, self.rb, self.ra, self.userdata, 32,
+                                              C.byref(self.cfg), C.byref(out), C.byref(words), C.byref(err))
+        return self._finish(rc, err, out, words, keep=True)
+
     def prepare_host(self, pinned=True):
         torch = self.torch
         self.host, made = [], []
@@ -418,6 +425,7 @@ def main():
     ap.add_argument("--workload", default="U20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workers", type=int, default=0, help="proofs in flight per GPU (worker contexts); 0 = 3")
+    ap.add_argument("--no-in-segment", action="store_true", help="N > 1: skip the in-segment sharding measurement")
     ap.add_argument("--host-memory", default="pinned", choices=["pinned", "pageable"],
                     help="e2e leg: where the caller's trace columns live (the reference's Vec<F> columns are pageable)")
     args = ap.parse_args()
@@ -538,10 +546,42 @@ def main():
     barrier()
     for w in workers:
         w.close()
+    # ---- latency of ONE proof on one GPU (one context, nothing else in flight) ----
+    barrier()
+    t_single = seg.timed(lambda: [seg.step_device() for _ in range(args.steps)]) / args.steps
+    # ---- in-segment sharding (north_star): groups of min(N, 4) GPUs prove ONE segment together ----
+    in_segment = None
+    if world > 1 and not args.no_in_segment:
+        import hashlib
+        from zkm_b200 import multi
+        gi, ri, g = multi.shard_group_init(lib)
+        del segs[1:]
+        torch.cuda.empty_cache()
+        sseg = Segment(lib, args.workload, seed_offset=1000 + gi, rank=rank, world=world)      # same traces on every rank of a group
+        for _ in range(2):
+            sseg.step_device()
+        barrier()
+        t_shard = sseg.timed(lambda: [sseg.step_device() for _ in range(args.steps)]) / args.steps
+        proof = sseg.step_device_keep()
+        barrier()
+        multi.shard_group_shutdown(lib)
+        ref = sseg.step_device_keep() if ri == 0 else None       # the same segment proved by one GPU alone
+        digest = hashlib.sha256(proof.tobytes()).digest()
+        same_as_single = (hashlib.sha256(ref.tobytes()).digest() == digest) if ref is not None else True
+        dg = torch.tensor(list(digest) + [int(same_as_single)], dtype=torch.uint8, device="cuda")
+        alld = [torch.zeros_like(dg) for _ in range(world)]
+        dist.all_gather(alld, dg)
+        ts = torch.tensor([t_shard], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        groups = world // g
+        ok = all(bool((alld[r][:32] == alld[(r // g) * g][:32]).all()) for r in range(world)) and all(bool(a[32]) for a in alld)
+        in_segment = {"group_size": g, "groups": groups, "ms_per_proof": float(ts.item()), "proofs_per_s": groups / (float(ts.item()) * 1e-3),
+                      "exchange": "NCCL: cap all-gather per commitment (512 B), quotient halves broadcast, FRI query answers all-gather",
+                      "proofs_identical_across_ranks_and_to_single_gpu": ok}
     if world > 1:
-        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([t_dev, t_e2e, t_single], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = t.tolist()
+        t_dev, t_e2e, t_single = t.tolist()
     if rank == 0:
         peak, peak_kind = peaks()
         total_ms = sum(v["ms"] for v in fam.values()) or 1.0
@@ -585,7 +625,11 @@ def main():
                 "kernel_families": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                                         "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else 0.0),
                                         "share": v["ms"] / total_ms} for k, v in fam.items()},
+                "single_proof_latency_ms": t_single,
                 "clocks": clk.summary()}
+        if in_segment:
+            in_segment["speedup_vs_one_gpu"] = t_single / in_segment["ms_per_proof"]
+            line["in_segment"] = in_segment
         if "ntt_pass" in fam:
             line["roofline_ntt"] = roof("ntt_pass", fam["ntt_pass"], notes["ntt_pass"])
         hashing = [fam[k] for k in ("leaf_hash", "merkle_levels", "leaf_hash_rows") if k in fam]

@@ -92,6 +92,16 @@ int zkm_b200_timer_stop(double* ms, char** err);
 void zkm_b200_profile_enable(int on);
 int zkm_b200_profile_reset(char** err);
 int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, double* bytes, char** err);
+/* Timings keyed by the reference's TimingTree scope strings (prover.rs:146 "compute all trace commitments", :152 "compute trace
+ * commitment for {Table:?}", :204 "compute all proofs given commitments", :250-411 "prove {..} STARK", :513 "compute auxiliary
+ * polynomials commitment", :545 "compute quotient polys", :578 "compute quotient commitment", :620 "compute openings proof";
+ * the reference's :193 "compute CTL data" and :479 "compute lookup helper columns" are one scope per table here, and
+ * "compute openings" brackets StarkOpeningSet::new).  When enabled, every prove call records CUDA events at the scope
+ * boundaries; zkm_b200_last_timing returns the scopes of the calling thread's last proof as malloc'ed text, one line per scope
+ * in opening order: "<depth>\t<milliseconds of device time>\t<scope>\n" (release with zkm_b200_free_string).  The Rust shim
+ * logs them next to the TimingTree it was handed (a TimingTree cannot be given durations from outside). */
+void zkm_b200_timing_enable(int on);
+char* zkm_b200_last_timing(void);
 /* Second per-family counter: bytes moved by the shared-memory passes for "ntt_pass" (16 B per element per pass), Poseidon
  * permutations for the hashing families ("leaf_hash", "merkle_levels", "leaf_hash_rows"), 0 elsewhere. */
 int zkm_b200_profile_get_traffic(const char* family, double* aux, char** err);
@@ -169,6 +179,43 @@ int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const
                                  const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata,
                                  uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
                                  char** err);
+
+/* ---- column-layout handshake ---------------------------------------------------------------------------------------
+ *
+ * The constraint kernels address trace columns by index.  Those indices are the memory layout of the reference's column
+ * structs: `CpuColumnsView` is #[repr(C)] (cpu/columns/mod.rs:68-118), but its 102-wide `general` union overlays nine
+ * views that are NOT #[repr(C)] (cpu/columns/general.rs:8-18,143-201), so their field order is formally up to rustc.  The Rust
+ * shim therefore reports where its compiler actually put every field this library reads -- (key, value) pairs taken from
+ * `COL_MAP` (mod.rs:184-189) and from `NUM_*_COLUMNS` -- and zkm_b200_layout_check compares them with the constants the
+ * kernels were compiled with (zkm_b200/csrc/tables/*.h).  A mismatch is an error naming the key, before any proof is made.
+ * Keys: ZKM_LK_NUM_COLUMNS + t = number of trace columns of table t (Table enum order, all_stark.rs:97-110); the CPU keys
+ * below are absolute column indices, except the *_REL keys, which are relative to ZKM_LK_CPU_GENERAL resp. to the start of
+ * one memory channel. */
+typedef enum {
+    ZKM_LK_NUM_COLUMNS = 0,                 /* + table index 0..11 */
+    ZKM_LK_CPU_IS_BOOTSTRAP_KERNEL = 100, ZKM_LK_CPU_IS_EXIT_KERNEL, ZKM_LK_CPU_CONTEXT, ZKM_LK_CPU_CODE_CONTEXT,
+    ZKM_LK_CPU_PROGRAM_COUNTER, ZKM_LK_CPU_NEXT_PROGRAM_COUNTER, ZKM_LK_CPU_IS_KERNEL_MODE,
+    ZKM_LK_CPU_OP_BINARY_OP /* first op flag */, ZKM_LK_CPU_OP_SYSCALL /* last op flag */,
+    ZKM_LK_CPU_BRANCH_SHOULD_JUMP, ZKM_LK_CPU_BRANCH_IS_NE,
+    ZKM_LK_CPU_OPCODE_BITS, ZKM_LK_CPU_RS_BITS, ZKM_LK_CPU_RT_BITS, ZKM_LK_CPU_RD_BITS, ZKM_LK_CPU_SHAMT_BITS, ZKM_LK_CPU_FUNC_BITS,
+    ZKM_LK_CPU_IS_POSEIDON_SPONGE, ZKM_LK_CPU_IS_KECCAK_SPONGE, ZKM_LK_CPU_IS_SHA_EXTEND_SPONGE, ZKM_LK_CPU_IS_SHA_COMPRESS_SPONGE,
+    ZKM_LK_CPU_GENERAL, ZKM_LK_CPU_MEMIO_IS_LH, ZKM_LK_CPU_MEMIO_AUX_FILTER, ZKM_LK_CPU_CLOCK, ZKM_LK_CPU_MEM_CHANNELS,
+    ZKM_LK_CPU_MEM_CHANNEL_STRIDE,          /* columns per MemoryChannelView */
+    ZKM_LK_CPU_CH_USED_REL, ZKM_LK_CPU_CH_IS_READ_REL, ZKM_LK_CPU_CH_ADDR_CONTEXT_REL, ZKM_LK_CPU_CH_ADDR_SEGMENT_REL,
+    ZKM_LK_CPU_CH_ADDR_VIRTUAL_REL, ZKM_LK_CPU_CH_VALUE_REL,
+    ZKM_LK_CPU_G_SYSCALL_COND_REL = 200, ZKM_LK_CPU_G_SYSCALL_SYSNUM_REL, ZKM_LK_CPU_G_SYSCALL_A0_REL, ZKM_LK_CPU_G_SYSCALL_A1_REL,
+    ZKM_LK_CPU_G_MISC_RS_BITS_REL, ZKM_LK_CPU_G_MISC_IS_MSB_REL, ZKM_LK_CPU_G_MISC_IS_LSB_REL, ZKM_LK_CPU_G_MISC_AUXM_REL,
+    ZKM_LK_CPU_G_MISC_AUXL_REL, ZKM_LK_CPU_G_MISC_AUXS_REL, ZKM_LK_CPU_G_MISC_RD_INDEX_REL, ZKM_LK_CPU_G_MISC_RD_INDEX_EQ_0_REL,
+    ZKM_LK_CPU_G_MISC_RD_INDEX_EQ_29_REL,
+    ZKM_LK_CPU_G_IO_RS_LE_REL, ZKM_LK_CPU_G_IO_RT_LE_REL, ZKM_LK_CPU_G_IO_MEM_LE_REL, ZKM_LK_CPU_G_IO_AUX_RS0_MUL_RS1_REL,
+    ZKM_LK_CPU_G_LOGIC_DIFF_PINV_REL, ZKM_LK_CPU_G_HASH_VALUE_REL, ZKM_LK_CPU_G_KHASH_VALUE_REL, ZKM_LK_CPU_G_SHASH_VALUE_REL,
+    ZKM_LK_CPU_G_ELEMENT_VALUE_REL
+} zkm_layout_key_t;
+/* pairs = n_pairs x (key, value).  Needs no device and no zkm_b200_init.  Returns -1 with a message naming the first
+ * mismatching key (or an unknown key). */
+int zkm_b200_layout_check(const uint32_t* pairs, size_t n_pairs, char** err);
+/* The library's own view: writes up to max_pairs (key, value) pairs for every key above, returns their number in *n_pairs. */
+int zkm_b200_layout_describe(uint32_t* pairs, size_t max_pairs, size_t* n_pairs, char** err);
 
 /* ---- staged API (stage-by-stage parity against the oracle) ------------------------------- */
 

@@ -73,3 +73,38 @@ def test_transcript_permutation_matches_oracle(orc):
     assert lib.zkm_b200_transcript_permute(u64ptr(got), n, C.byref(err)) == 0
     assert (got == want).all()
     assert int(got[0, 0]) == 0x3c18a9786cb0b359 and int(got[1, 0]) == 0xd64e1e3efc5b8e9e
+
+
+def test_column_layout_handshake_against_reference_derived_fixture():
+    """tests/golden/column_layout_v1.json holds the CPU-table field offsets derived from the REFERENCE's struct declarations
+    (tools/gen_layout_golden.py, run where /root/reference exists) as the (key, value) pairs of the layout handshake
+    (include/zkm_b200.h): the constants the kernels were compiled with must agree with every one of them, and a shifted
+    field must be reported by key.  This is the call the Rust shim makes with the offsets of ITS compiler before proving."""
+    import json
+    from zkm_b200.lib import load
+    lib = load()
+    g = json.loads((ROOT / "tests/golden/column_layout_v1.json").read_text())
+    pairs = g["pairs"]
+    assert len(pairs) >= 60
+    flat = [x for p in pairs for x in p]
+    arr = (C.c_uint32 * len(flat))(*flat)
+    err = C.c_void_p()
+    assert lib.zkm_b200_layout_check(arr, len(pairs), C.byref(err)) == 0, C.cast(err, C.c_char_p).value
+    # the library's own description covers exactly the fixture's keys with the same values
+    n = C.c_size_t()
+    out = (C.c_uint32 * 512)()
+    assert lib.zkm_b200_layout_describe(out, 256, C.byref(n), C.byref(err)) == 0
+    mine = {out[2 * i]: out[2 * i + 1] for i in range(n.value)}
+    assert mine == {k: v for k, v in pairs}
+    # a rustc that had reordered CpuMiscView (rd_index <-> auxs) must be caught
+    k = g["keys"]["ZKM_LK_CPU_G_MISC_AUXS_REL"]
+    bad = [(a, b + 1 if a == k else b) for a, b in pairs]
+    flat = [x for p in bad for x in p]
+    arr = (C.c_uint32 * len(flat))(*flat)
+    assert lib.zkm_b200_layout_check(arr, len(bad), C.byref(err)) == -1
+    msg = C.cast(err, C.c_char_p).value.decode()
+    lib.zkm_b200_free_string(err)
+    assert f"key {k}" in msg and "mismatch" in msg
+    unknown = (C.c_uint32 * 2)(9999, 1)
+    assert lib.zkm_b200_layout_check(unknown, 1, C.byref(err)) == -1
+    lib.zkm_b200_free_string(err)

@@ -125,6 +125,13 @@ int zkm_b200_profile_get(const char* family, double* ms, uint64_t* launches, dou
     if (!ok) throw std::runtime_error(std::string("no such kernel family: ") + family);
     ZKM_API_END
 }
+void zkm_b200_timing_enable(int on) { scopes_enable(on != 0); }
+char* zkm_b200_last_timing(void) {
+    const std::string& t = scopes_last();
+    char* m = (char*)malloc(t.size() + 1);
+    if (m) memcpy(m, t.c_str(), t.size() + 1);
+    return m;
+}
 int zkm_b200_profile_get_traffic(const char* family, double* aux, char** err) {
     ZKM_API_BEGIN
     double a = 0;
@@ -449,6 +456,69 @@ int zkm_b200_prove_with_trace_rows(const zkm_table_t* tables, const zkm_table_ro
     ZKM_API_END
 }
 
+
+// ---- column-layout handshake (include/zkm_b200.h): the offsets the kernels were compiled with
+static std::vector<std::pair<uint32_t, uint32_t>> layout_pairs() {
+    namespace c = tables::cpu;
+    std::vector<std::pair<uint32_t, uint32_t>> v;
+    for (int t = 0; t < tables::NUM_TABLE_KINDS; t++) v.push_back({(uint32_t)(ZKM_LK_NUM_COLUMNS + t), (uint32_t)tables::table_num_columns(t)});
+    auto add = [&](zkm_layout_key_t k, int val) { v.push_back({(uint32_t)k, (uint32_t)val}); };
+    add(ZKM_LK_CPU_IS_BOOTSTRAP_KERNEL, c::IS_BOOTSTRAP_KERNEL); add(ZKM_LK_CPU_IS_EXIT_KERNEL, c::IS_EXIT_KERNEL);
+    add(ZKM_LK_CPU_CONTEXT, c::CONTEXT); add(ZKM_LK_CPU_CODE_CONTEXT, c::CODE_CONTEXT);
+    add(ZKM_LK_CPU_PROGRAM_COUNTER, c::PROGRAM_COUNTER); add(ZKM_LK_CPU_NEXT_PROGRAM_COUNTER, c::NEXT_PROGRAM_COUNTER);
+    add(ZKM_LK_CPU_IS_KERNEL_MODE, c::IS_KERNEL_MODE);
+    add(ZKM_LK_CPU_OP_BINARY_OP, c::OP_BINARY_OP); add(ZKM_LK_CPU_OP_SYSCALL, c::OP_SYSCALL);
+    add(ZKM_LK_CPU_BRANCH_SHOULD_JUMP, c::BR_SHOULD_JUMP); add(ZKM_LK_CPU_BRANCH_IS_NE, c::BR_IS_NE);
+    add(ZKM_LK_CPU_OPCODE_BITS, c::OPCODE_BITS); add(ZKM_LK_CPU_RS_BITS, c::RS_BITS); add(ZKM_LK_CPU_RT_BITS, c::RT_BITS);
+    add(ZKM_LK_CPU_RD_BITS, c::RD_BITS); add(ZKM_LK_CPU_SHAMT_BITS, c::SHAMT_BITS); add(ZKM_LK_CPU_FUNC_BITS, c::FUNC_BITS);
+    add(ZKM_LK_CPU_IS_POSEIDON_SPONGE, c::IS_POSEIDON_SPONGE); add(ZKM_LK_CPU_IS_KECCAK_SPONGE, c::IS_KECCAK_SPONGE);
+    add(ZKM_LK_CPU_IS_SHA_EXTEND_SPONGE, c::IS_SHA_EXTEND_SPONGE); add(ZKM_LK_CPU_IS_SHA_COMPRESS_SPONGE, c::IS_SHA_COMPRESS_SPONGE);
+    add(ZKM_LK_CPU_GENERAL, c::GENERAL); add(ZKM_LK_CPU_MEMIO_IS_LH, c::MEMIO_IS_LH); add(ZKM_LK_CPU_MEMIO_AUX_FILTER, c::MEMIO_AUX_FILTER);
+    add(ZKM_LK_CPU_CLOCK, c::CLOCK); add(ZKM_LK_CPU_MEM_CHANNELS, c::MEM_CHANNELS);
+    add(ZKM_LK_CPU_MEM_CHANNEL_STRIDE, c::ch(1, 0) - c::ch(0, 0));
+    add(ZKM_LK_CPU_CH_USED_REL, c::CH_USED); add(ZKM_LK_CPU_CH_IS_READ_REL, c::CH_IS_READ);
+    add(ZKM_LK_CPU_CH_ADDR_CONTEXT_REL, c::CH_ADDR_CONTEXT); add(ZKM_LK_CPU_CH_ADDR_SEGMENT_REL, c::CH_ADDR_SEGMENT);
+    add(ZKM_LK_CPU_CH_ADDR_VIRTUAL_REL, c::CH_ADDR_VIRTUAL); add(ZKM_LK_CPU_CH_VALUE_REL, c::CH_VALUE);
+    const int G = c::GENERAL;
+    add(ZKM_LK_CPU_G_SYSCALL_COND_REL, c::G_SYSCALL_COND - G); add(ZKM_LK_CPU_G_SYSCALL_SYSNUM_REL, c::G_SYSCALL_SYSNUM - G);
+    add(ZKM_LK_CPU_G_SYSCALL_A0_REL, c::G_SYSCALL_A0 - G); add(ZKM_LK_CPU_G_SYSCALL_A1_REL, c::G_SYSCALL_A1 - G);
+    add(ZKM_LK_CPU_G_MISC_RS_BITS_REL, c::G_MISC_RS_BITS - G); add(ZKM_LK_CPU_G_MISC_IS_MSB_REL, c::G_MISC_IS_MSB - G);
+    add(ZKM_LK_CPU_G_MISC_IS_LSB_REL, c::G_MISC_IS_LSB - G); add(ZKM_LK_CPU_G_MISC_AUXM_REL, c::G_MISC_AUXM - G);
+    add(ZKM_LK_CPU_G_MISC_AUXL_REL, c::G_MISC_AUXL - G); add(ZKM_LK_CPU_G_MISC_AUXS_REL, c::G_MISC_AUXS - G);
+    add(ZKM_LK_CPU_G_MISC_RD_INDEX_REL, c::G_MISC_RD_INDEX - G); add(ZKM_LK_CPU_G_MISC_RD_INDEX_EQ_0_REL, c::G_MISC_RD_INDEX_EQ_0 - G);
+    add(ZKM_LK_CPU_G_MISC_RD_INDEX_EQ_29_REL, c::G_MISC_RD_INDEX_EQ_29 - G);
+    add(ZKM_LK_CPU_G_IO_RS_LE_REL, c::G_IO_RS_LE - G); add(ZKM_LK_CPU_G_IO_RT_LE_REL, c::G_IO_RT_LE - G);
+    add(ZKM_LK_CPU_G_IO_MEM_LE_REL, c::G_IO_MEM_LE - G); add(ZKM_LK_CPU_G_IO_AUX_RS0_MUL_RS1_REL, c::G_IO_AUX_RS0_MUL_RS1 - G);
+    add(ZKM_LK_CPU_G_LOGIC_DIFF_PINV_REL, c::G_LOGIC_DIFF_PINV - G); add(ZKM_LK_CPU_G_HASH_VALUE_REL, c::G_HASH_VALUE - G);
+    add(ZKM_LK_CPU_G_KHASH_VALUE_REL, c::G_KHASH_VALUE - G); add(ZKM_LK_CPU_G_SHASH_VALUE_REL, c::G_SHASH_VALUE - G);
+    add(ZKM_LK_CPU_G_ELEMENT_VALUE_REL, c::G_ELEMENT_VALUE - G);
+    return v;
+}
+int zkm_b200_layout_check(const uint32_t* pairs, size_t n_pairs, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(pairs || n_pairs == 0, "null argument");
+    auto mine = layout_pairs();
+    for (size_t i = 0; i < n_pairs; i++) {
+        const uint32_t key = pairs[2 * i], val = pairs[2 * i + 1];
+        bool found = false;
+        for (auto& kv : mine)
+            if (kv.first == key) {
+                found = true;
+                ZKM_CHECK(kv.second == val, "column layout mismatch at key " + std::to_string(key) + ": the caller has " + std::to_string(val) +
+                                                ", the kernels were compiled with " + std::to_string(kv.second));
+            }
+        ZKM_CHECK(found, "unknown layout key " + std::to_string(key));
+    }
+    ZKM_API_END
+}
+int zkm_b200_layout_describe(uint32_t* pairs, size_t max_pairs, size_t* n_pairs, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(n_pairs, "null argument");
+    auto mine = layout_pairs();
+    *n_pairs = mine.size();
+    for (size_t i = 0; i < mine.size() && i < max_pairs && pairs; i++) { pairs[2 * i] = mine[i].first; pairs[2 * i + 1] = mine[i].second; }
+    ZKM_API_END
+}
 
 void zkm_b200_batch_free(zkm_batch_t* b) {
     if (!b) return;

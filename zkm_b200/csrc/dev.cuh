@@ -86,6 +86,20 @@ bool prof_get(const char* name, double* ms, unsigned long long* launches, double
 // Names seen so far, '\n'-separated.
 std::string prof_names();
 
+// Timings keyed by the reference's TimingTree scope strings (prover.rs:86,146,152,193,204,250..411,479,513,545,562,578,620):
+// the reference times nested wall-clock scopes on the host; here every scope is bracketed by CUDA events on the launching
+// stream, so the figure is the device time of that scope.  Off by default (zkm_b200_timing_enable); resolved once per proof.
+struct TimedScope {
+    cudaStream_t s; int idx = -1;
+    TimedScope(const std::string& name, cudaStream_t s_);
+    ~TimedScope();
+    TimedScope(const TimedScope&) = delete;
+};
+void scopes_enable(bool on);
+void scopes_begin();                       // start of a proof on this thread's context
+void scopes_finish();                      // end of the proof: resolves the events into the text returned by scopes_last()
+const std::string& scopes_last();          // "<depth>\t<ms>\t<scope name>\n" per scope, in opening order
+
 // Row-major n x ncols block -> column-major ncols x n (transpose.cu).
 void transpose_rows_to_cols(const u64* rows, u64* cols, size_t n, int ncols, cudaStream_t s);
 

@@ -5,6 +5,7 @@
 #include <map>
 #include <vector>
 #include <mutex>
+#include <cstdio>
 
 namespace zkm {
 
@@ -64,6 +65,52 @@ bool prof_get(const char* name, double* ms, unsigned long long* launches, double
     if (aux) *aux = it->second.aux;
     return true;
 }
+// ---- reference-scope timings (TimedScope, dev.cuh): CUDA events at the scope boundaries on the launching stream, resolved
+// when the proof has finished; one record list per host thread (= per context: a context is driven by one thread).
+namespace {
+bool g_scopes_on = false;
+struct ScopeRec { std::string name; int depth; cudaEvent_t e0, e1; };
+thread_local std::vector<ScopeRec> t_scopes;
+thread_local int t_depth = 0;
+thread_local std::string t_last_timing;
+}
+void scopes_enable(bool on) { g_scopes_on = on; }
+TimedScope::TimedScope(const std::string& name, cudaStream_t s_) : s(s_) {
+    if (!g_scopes_on) return;
+    idx = (int)t_scopes.size();
+    ScopeRec r{name, t_depth++, nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        r.e0 = get_event(); r.e1 = get_event();
+    }
+    cudaEventRecord(r.e0, s);
+    t_scopes.push_back(r);
+}
+TimedScope::~TimedScope() {
+    if (idx < 0) return;
+    cudaEventRecord(t_scopes[idx].e1, s);
+    t_depth--;
+}
+void scopes_begin() { scopes_finish(); t_last_timing.clear(); }
+void scopes_finish() {
+    if (t_scopes.empty()) return;
+    std::string out;
+    for (ScopeRec& r : t_scopes) {
+        cudaEventSynchronize(r.e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        char buf[64];
+        snprintf(buf, sizeof buf, "%d\t%.4f\t", r.depth, ms);
+        out += buf; out += r.name; out += "\n";
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_pool.push_back(r.e0); g_pool.push_back(r.e1);
+    }
+    t_scopes.clear();
+    t_depth = 0;
+    t_last_timing = out;
+}
+const std::string& scopes_last() { return t_last_timing; }
+
 std::string prof_names() {
     std::lock_guard<std::mutex> lk(g_mu);
     resolve();

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 
 namespace zkm {
 
@@ -113,6 +114,15 @@ struct TableJob {
     Batch trace;
 };
 
+// the table names the reference's scope strings use (prover.rs:250-411 "prove {} STARK")
+static const char* reference_scope_name(int kind) {
+    static const char* N[tables::NUM_TABLE_KINDS] = {"Arithmetic", "CPU", "Poseidon", "Poseidon sponge", "Keccak", "Keccak sponge", "SHA Extend",
+                                                     "SHA Extend sponge", "SHA Compress", "SHA Compress sponge", "Logic", "Memory"};
+    return kind >= 0 && kind < tables::NUM_TABLE_KINDS ? N[kind] : "?";
+}
+// `Table` Debug names (all_stark.rs:97-110), as in "compute trace commitment for {:?}" (prover.rs:152)
+static const char* reference_table_debug_name(int kind) { return tables::table_name(kind); }
+
 static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChallenges& ctl_ch, HostChallenger& ch, ProofWriter& W) {
     Ctx& c = ctx();
     cudaStream_t s = c.stream;
@@ -128,6 +138,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     u64 init_state[12];
     ch.compact(init_state);
     PhaseTimer pt(s, tables::table_name(job.kind));
+    TimedScope ts_table(std::string("prove ") + reference_scope_name(job.kind) + " STARK", s);      // prover.rs:250..411
 
     // ---- auxiliary polynomials (prover.rs:469-522)
     DProgram prog;
@@ -138,8 +149,14 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     Batch aux;
     {
         DevBuf auxv((size_t)naux * n, s);
-        compute_aux_columns(prog, L, job.values.p, log_n, ctl_ch, auxv.p, s);
+        {
+            // the reference builds the CTL columns of all tables up front ("compute CTL data", prover.rs:193) and the logUp
+            // columns per table (:479); here both are one pass over this table's trace
+            TimedScope ts("compute CTL data + lookup helper columns", s);
+            compute_aux_columns(prog, L, job.values.p, log_n, ctl_ch, auxv.p, s);
+        }
         job.values.release();
+        TimedScope ts("compute auxiliary polynomials commitment", s);                                 // prover.rs:513
         batch_from_values_dev(aux, std::move(auxv), naux, log_n, cfg.rate_bits, cfg.cap_height);
     }
     pt.mark("aux columns+commit");
@@ -151,9 +168,13 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     Batch quot;
     {
         DevBuf q((size_t)na * 2 * n, s);
-        compute_quotient_values(job.kind, prog, L, job.trace, aux, ctl_ch, alphas.data(), na, q.p, s);
-        coset_intt(c.ntt, q.p, 2 * n, q.p, 2 * n, na, log_n + 1, s);
-        // column a, chunk k (n coefficients) is polynomial 2a + k: already contiguous
+        {
+            TimedScope ts("compute quotient polys", s);                                               // prover.rs:545
+            compute_quotient_values(job.kind, prog, L, job.trace, aux, ctl_ch, alphas.data(), na, q.p, s);
+            coset_intt(c.ntt, q.p, 2 * n, q.p, 2 * n, na, log_n + 1, s);
+        }
+        // "split quotient polys" (prover.rs:562): column a, chunk k (n coefficients) is polynomial 2a + k: already contiguous
+        TimedScope ts("compute quotient commitment", s);                                              // prover.rs:578
         batch_from_coeffs_dev(quot, std::move(q), 2 * na, log_n, cfg.rate_bits, cfg.cap_height);
     }
     pt.mark("quotient+commit");
@@ -169,6 +190,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     std::vector<gl2> local_values(C), next_values(C), aux_local(naux), aux_next(naux), quot_open(Q);
     std::vector<gl> ctl_zs_first(nz);
     {
+        TimedScope ts("compute openings", s);                          // StarkOpeningSet::new (prover.rs:601; untimed upstream)
         gl2 pts[3] = {zeta, zeta_next, gl2::one()};
         std::vector<u64> h((size_t)std::max(std::max(C, naux), Q) * 3 * 2);
         eval_polys_at_points(job.trace.coeffs.p, C, log_n, pts, 2, h.data(), s);
@@ -195,6 +217,7 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     for (gl x : ctl_zs_first) ch.observe(gl2(x));
 
     // ---- FRI (prover.rs:618-628)
+    TimedScope ts_fri("compute openings proof", s);                                                   // prover.rs:620
     gl2 alpha = ch.get_ext_challenge();
     const int K0 = C + naux + Q, K1 = C + naux;
     std::vector<gl2> apow(K0);
@@ -363,6 +386,9 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
     std::vector<tables::TableLayout> layout = tables::derive_layout(sys, cfg.num_challenges);
     std::vector<TableJob> jobs(inputs.size());
     PhaseTimer pt0(s, "all");
+    scopes_begin();
+    struct ScopesEnd { ~ScopesEnd() { scopes_finish(); } } scopes_end;       // also on the error paths
+    std::unique_ptr<TimedScope> ts_commit(new TimedScope("compute all trace commitments", s));        // prover.rs:146
     // trace commitments (prover.rs:144-167)
     // The 12 commitments are independent (their caps enter the transcript afterwards, in table order), so they run smallest
     // table first: with host inputs the uploader streams the tables in this same order (capi.cu) and the large tables arrive
@@ -379,6 +405,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
         ZKM_CHECK(j.log_n + (int)cfg.rate_bits >= (int)cfg.cap_height && j.log_n >= 1, "trace too short");
         size_t n = (size_t)1 << j.log_n;
         j.values = std::move(inputs[t].values);
+        TimedScope ts(std::string("compute trace commitment for ") + reference_table_debug_name(j.kind), s);   // prover.rs:152
         DevBuf coeffs((size_t)j.layout.ncols * n, s);
         if (!inputs[t].group_ends.empty()) {
             TableInput& in = inputs[t];
@@ -395,6 +422,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
         batch_from_coeffs_dev(j.trace, std::move(coeffs), j.layout.ncols, j.log_n, cfg.rate_bits, cfg.cap_height);
     }
     pt0.mark("trace commitments");
+    ts_commit.reset();
     HostChallenger ch;
     for (TableJob& j : jobs) ch.observe_cap(j.trace.tree.cap);
     for (int i = 0; i < 8; i++) ch.observe((u64)pv.roots_before[i]);
@@ -412,9 +440,12 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
     for (int i = 0; i < 8; i++) W.u(pv.roots_after[i]);
     W.u(pv.userdata.size());
     for (uint8_t b : pv.userdata) W.u(b);
-    for (TableJob& j : jobs) {
-        prove_single_table(j, cfg, ctl, ch, W);
-        j.trace = Batch();                                      // release this table's device memory
+    {
+        TimedScope ts("compute all proofs given commitments", s);                                    // prover.rs:204
+        for (TableJob& j : jobs) {
+            prove_single_table(j, cfg, ctl, ch, W);
+            j.trace = Batch();                                  // release this table's device memory
+        }
     }
     ZKM_CUDA(cudaStreamSynchronize(s));
     return std::move(W.w);

@@ -36,7 +36,7 @@ EXPORTS = [
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_profile_families",
 ]
 
 
@@ -95,6 +95,10 @@ def load():
     lib.zkm_b200_shard_shutdown.argtypes = [C.POINTER(C.c_void_p)]
     lib.zkm_b200_profile_get_traffic.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
     lib.zkm_b200_profile_families.restype = C.c_void_p
+    lib.zkm_b200_layout_check.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.zkm_b200_layout_describe.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_timing_enable.argtypes = [C.c_int]
+    lib.zkm_b200_last_timing.restype = C.c_void_p
     del errp
     _lib = lib
     return lib

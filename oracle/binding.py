@@ -54,6 +54,10 @@ def load():
     lib.orc_verify_system.argtypes = [C.c_int, u64p, C.c_size_t, C.POINTER(C.c_uint32)]
     lib.orc_check_table_constraints.restype = C.c_long
     lib.orc_check_table_constraints.argtypes = [C.c_int, C.POINTER(u64p), C.c_uint32, C.c_uint32]
+    lib.orc_table_fingerprint.argtypes = [C.c_int, u64, u64p]
+    lib.orc_ctl_fingerprint.argtypes = [C.c_int, C.c_int, C.c_int, u64, u64p]
+    lib.orc_num_ctls.argtypes = [C.c_int]
+    lib.orc_lookup_fingerprint.argtypes = [C.c_int, C.c_int, u64, u64p]
     lib.orc_gen_poseidon_rows.argtypes = [u64p, u64p, C.c_size_t, u64p]
     _lib = lib
     return lib

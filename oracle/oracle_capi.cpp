@@ -239,4 +239,90 @@ void orc_gen_poseidon_rows(const uint64_t* inputs, const uint64_t* timestamps, s
     });
 }
 
+
+// ---- transcription fingerprints (tests/golden/constraint_fingerprints_v1.json; INTEGRATION.md section 3 holds the Rust test
+// that prints the same numbers from eval_packed_generic / all_cross_table_lookups on the reference side).
+// Rows: cell c of the local row = fp_cell(seed + 2c), of the next row = fp_cell(seed + 2c + 1), SplitMix64 reduced mod p.
+static inline uint64_t fp_cell(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return z % GL_P;
+}
+static const uint64_t FP_ALPHA0 = 0x9E3779B97F4A7C15ULL % GL_P, FP_ALPHA1 = 0xC2B2AE3D27D4EB4FULL % GL_P;
+struct CountingConsumer : Consumer<Fp> {
+    uint64_t count = 0;
+    CountingConsumer() : Consumer<Fp>({Fp(FP_ALPHA0), Fp(FP_ALPHA1)}, Fp(3), Fp(5), Fp(7)) {}
+    void constraint(Fp c) { count++; Consumer<Fp>::constraint(c); }
+    void constraint_transition(Fp c) { constraint(c * z_last); }
+    void constraint_first_row(Fp c) { constraint(c * l_first); }
+    void constraint_last_row(Fp c) { constraint(c * l_last); }
+};
+static void fp_rows(uint64_t seed, int ncols, std::vector<Fp>& lv, std::vector<Fp>& nv) {
+    lv.resize(ncols); nv.resize(ncols);
+    for (int c = 0; c < ncols; c++) { lv[c] = Fp(fp_cell(seed + 2 * (uint64_t)c)); nv[c] = Fp(fp_cell(seed + 2 * (uint64_t)c + 1)); }
+}
+// All constraints of table `kind` (the reference's eval_packed_generic, emission order) on one pseudo-random frame, folded
+// acc <- acc * alpha + c with alphas (FP_ALPHA0, FP_ALPHA1), z_last = 3, lagrange_first = 5, lagrange_last = 7
+// (constraint_consumer.rs:52-75).  out = {number of constraints, acc0, acc1}.  An omitted, added or reordered constraint, a
+// wrong column or a wrong coefficient changes acc.
+int orc_table_fingerprint(int kind, uint64_t seed, uint64_t out[3]) {
+    try {
+        std::vector<Fp> lv, nv;
+        fp_rows(seed, zkm::tables::table_num_columns(kind), lv, nv);
+        CountingConsumer yc;
+        RowView<Fp> l{lv.data()}, nx{nv.data()};
+        if (!zkm::tables::eval_table<Fp, RowView<Fp>, CountingConsumer>(kind, l, nx, yc)) throw std::runtime_error("no constraints for this table");
+        out[0] = yc.count; out[1] = yc.accs[0].v; out[2] = yc.accs[1].v;
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// fold of (filter value, column values...) of one TableWithColumns on the frame above: acc <- acc * FP_ALPHA0 + v
+static Fp fp_table_with_columns(const zkm::tables::TableWithColumns& t, const Fp* lv, const Fp* nv) {
+    Fp acc = filter_eval<Fp>(t.filter, lv, nv);
+    for (const auto& c : t.columns) acc = acc * Fp(FP_ALPHA0) + col_eval_with_next<Fp>(c, lv, nv);
+    return acc;
+}
+// CTL number `ctl` of System `system_id` (all_stark.rs:136-542 for system 0).  entry < num_looking: that looking table, entry ==
+// num_looking: the looked table.  out = {table index in the System, number of columns, fingerprint}; returns the number of
+// looking tables, or -1.  The frame is seeded with seed + 0x10000 * table.
+int orc_ctl_fingerprint(int system_id, int ctl, int entry, uint64_t seed, uint64_t out[3]) {
+    try {
+        zkm::tables::System sys = zkm::tables::make_system(system_id);
+        if (ctl < 0 || ctl >= (int)sys.ctls.size()) throw std::runtime_error("no such CTL");
+        const auto& c = sys.ctls[ctl];
+        const int nl = (int)c.looking_tables.size();
+        if (entry < 0 || entry > nl) throw std::runtime_error("no such CTL entry");
+        const auto& t = entry < nl ? c.looking_tables[entry] : c.looked_table;
+        std::vector<Fp> lv, nv;
+        fp_rows(seed + 0x10000ULL * (uint64_t)t.table, zkm::tables::table_num_columns(sys.kinds[t.table]), lv, nv);
+        out[0] = (uint64_t)t.table; out[1] = t.columns.size(); out[2] = fp_table_with_columns(t, lv.data(), nv.data()).v;
+        return nl;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int orc_num_ctls(int system_id) {
+    try { return (int)zkm::tables::make_system(system_id).ctls.size(); } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// In-table logUp lookup number `idx` of table `kind` (lookup.rs:20-31; arithmetic_stark.rs:269-276, memory_stark.rs:476-483):
+// out = {number of looked-up columns, fingerprint over (columns..., table_column, frequencies_column, filters...)}; returns the
+// number of lookups of the table, or -1.
+int orc_lookup_fingerprint(int kind, int idx, uint64_t seed, uint64_t out[2]) {
+    try {
+        auto ls = zkm::tables::table_lookups(kind);
+        if (idx < 0 || idx >= (int)ls.size()) { out[0] = out[1] = 0; return (int)ls.size(); }
+        std::vector<Fp> lv, nv;
+        fp_rows(seed, zkm::tables::table_num_columns(kind), lv, nv);
+        const auto& l = ls[idx];
+        Fp acc = Fp(0);
+        auto push = [&](Fp v) { acc = acc * Fp(FP_ALPHA0) + v; };
+        for (const auto& c : l.columns) push(col_eval_with_next<Fp>(c, lv.data(), nv.data()));
+        push(col_eval_with_next<Fp>(l.table_column, lv.data(), nv.data()));
+        push(col_eval_with_next<Fp>(l.frequencies_column, lv.data(), nv.data()));
+        for (const auto& f : l.filter_columns) push(filter_eval<Fp>(f, lv.data(), nv.data()));
+        out[0] = l.columns.size(); out[1] = acc.v;
+        return (int)ls.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 }  // extern "C"

@@ -180,6 +180,19 @@ int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const
                                  uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
                                  char** err);
 
+/* ---- proof wire format -------------------------------------------------------------------------
+ *
+ * zkm_b200_proof_table_json writes what `serde_json::to_string(&all_proof.stark_proofs[table].proof)` gives for the reference's
+ * `StarkProof<F, C, D>` (proof.rs:177-189, #[derive(Serialize)]; the text whose length prove_segments logs as "proof size",
+ * prover/examples/utils/src/utils.rs:156-161): compact JSON, fields in declaration order -- trace_cap, auxiliary_polys_cap,
+ * quotient_polys_cap, openings {local_values, next_values, auxiliary_polys, auxiliary_polys_next, ctl_zs_first,
+ * quotient_polys}, opening_proof {commit_phase_merkle_caps, query_round_proofs [{initial_trees_proof {evals_proofs}, steps
+ * [{evals, merkle_proof {siblings}}]}], final_poly {coeffs}, pow_witness}; field elements are decimal u64, extension elements
+ * [a, b], digests {"elements":[..4..]}.  zkm_b200_public_values_json does the same for `PublicValues` (proof.rs:52-66; the
+ * file recursion/src/lib.rs:142-146 writes).  Host-only: no device, no zkm_b200_init.  Strings are malloc'ed (zkm_b200_free_string). */
+int zkm_b200_proof_table_json(const uint64_t* proof, size_t proof_words, uint32_t table, char** json_out, size_t* json_len, char** err);
+int zkm_b200_public_values_json(const uint64_t* proof, size_t proof_words, char** json_out, size_t* json_len, char** err);
+
 /* ---- column-layout handshake ---------------------------------------------------------------------------------------
  *
  * The constraint kernels address trace columns by index.  Those indices are the memory layout of the reference's column

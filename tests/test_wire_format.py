@@ -1,0 +1,95 @@
+"""Proof wire format: zkm_b200_proof_table_json must be the serde_json text of the reference's `StarkProof`
+(proof.rs:177-189) -- checked here structurally against an independent walk of the flat proof buffer (a proof made by the CPU
+oracle, so the test needs no GPU): field names and order, nesting, every number, compactness."""
+import json
+import re
+
+import numpy as np
+
+import traces as tr
+from oracle import binding
+from zkm_b200 import lib as zl
+
+MAGIC = 0x464F4F52504D4B5A
+
+
+class Walk:
+    def __init__(self, w):
+        self.w, self.p = [int(x) for x in w], 0
+
+    def u(self):
+        self.p += 1
+        return self.w[self.p - 1]
+
+    def words(self, n):
+        self.p += n
+        return self.w[self.p - n:self.p]
+
+    def vec(self, unit):
+        n = self.u()
+        x = self.words(n * unit)
+        return x if unit == 1 else [x[i * unit:(i + 1) * unit] for i in range(n)]
+
+
+def expected_tables(proof):
+    """The structure serde derives for AllProof.stark_proofs[t].proof, from the buffer layout of include/zkm_b200.h."""
+    r = Walk(proof)
+    assert r.u() == MAGIC and r.u() == 1
+    nt = r.u()
+    r.words(2 * r.u())
+    rb, ra = r.words(8), r.words(8)
+    ud = r.vec(1)
+    H = lambda hs: [{"elements": h} for h in hs]      # noqa: E731
+    out = []
+    for _ in range(nt):
+        r.words(12)
+        d = {"trace_cap": H(r.vec(4)), "auxiliary_polys_cap": H(r.vec(4)), "quotient_polys_cap": H(r.vec(4))}
+        d["openings"] = {"local_values": r.vec(2), "next_values": r.vec(2), "auxiliary_polys": r.vec(2),
+                         "auxiliary_polys_next": r.vec(2), "ctl_zs_first": r.vec(1), "quotient_polys": r.vec(2)}
+        caps = [H(r.vec(4)) for _ in range(r.u())]
+        rounds = []
+        for _ in range(r.u()):
+            ev = []
+            for _ in range(r.u()):
+                leaf = r.vec(1)
+                ev.append([leaf, {"siblings": H(r.vec(4))}])
+            steps = []
+            for _ in range(r.u()):
+                evals = r.vec(2)
+                steps.append({"evals": evals, "merkle_proof": {"siblings": H(r.vec(4))}})
+            rounds.append({"initial_trees_proof": {"evals_proofs": ev}, "steps": steps})
+        d["opening_proof"] = {"commit_phase_merkle_caps": caps, "query_round_proofs": rounds, "final_poly": {"coeffs": r.vec(2)},
+                              "pow_witness": r.u()}
+        out.append(d)
+    assert r.p == len(r.w)
+    return out, {"roots_before": {"root": rb}, "roots_after": {"root": ra}, "userdata": ud}
+
+
+def test_stark_proof_json_matches_the_serde_layout(orc):
+    lib = zl.load()
+    traces = [tr.poseidon_trace(orc, 6), tr.logic_trace(8), tr.memory_trace(7)]
+    proof = binding.prove_system(orc, tr.SYSTEM_MINI3, traces, roots_before=[3] * 8, userdata=bytes(range(32)))
+    want, want_pv = expected_tables(proof)
+    for t, w in enumerate(want):
+        s = zl.proof_table_json(lib, proof, t)
+        assert not re.search(r"\s", s)                                   # serde_json::to_string is compact
+        got = json.loads(s)
+        assert got == w
+        assert list(got.keys()) == ["trace_cap", "auxiliary_polys_cap", "quotient_polys_cap", "openings", "opening_proof"]
+        assert list(got["openings"].keys()) == ["local_values", "next_values", "auxiliary_polys", "auxiliary_polys_next", "ctl_zs_first",
+                                                "quotient_polys"]
+        assert list(got["opening_proof"].keys()) == ["commit_phase_merkle_caps", "query_round_proofs", "final_poly", "pow_witness"]
+        assert json.dumps(w, separators=(",", ":")) == s                  # byte for byte: same field order, no padding
+    pv = zl.public_values_json(lib, proof)
+    assert json.loads(pv) == want_pv and json.dumps(want_pv, separators=(",", ":")) == pv
+    assert want_pv["userdata"] == list(range(32)) and want_pv["roots_before"]["root"] == [3] * 8
+
+
+def test_json_errors():
+    import ctypes as C
+    lib = zl.load()
+    bad = np.zeros(8, dtype=np.uint64)
+    out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+    assert lib.zkm_b200_proof_table_json(zl.u64ptr(bad), bad.size, 0, C.byref(out), C.byref(n), C.byref(err)) == -1
+    assert b"magic" in C.cast(err, C.c_char_p).value
+    lib.zkm_b200_free_string(err)

@@ -1,0 +1,189 @@
+// Proof wire format: the serde_json text of the reference's proof structs, produced from the flat proof buffer.
+// Replaces `serde_json::to_string(&stark_proof)` for `StarkProof<F, C, D>` (reference prover/src/proof.rs:177-189,
+// #[derive(Serialize)]; used for the proof-size log at prover/examples/utils/src/utils.rs:156-161) and
+// `serde_json::to_string(&public_values)` for `PublicValues` (proof.rs:52-66; written to disk at recursion/src/lib.rs:142-146).
+// serde's derived encodings of the plonky2 0.1.4 types (not in /root/reference; restated):
+//   GoldilocksField(u64)             newtype -> the number (canonical u64, decimal)
+//   QuadraticExtension([F; 2])       newtype -> [a, b]
+//   HashOut { elements: [F; 4] }     -> {"elements":[e0,e1,e2,e3]}
+//   MerkleCap(Vec<HashOut>)          newtype -> [hash, ...]
+//   MerkleProof { siblings }         -> {"siblings":[hash, ...]}
+//   PolynomialCoeffs { coeffs }      -> {"coeffs":[...]}
+//   FriInitialTreeProof { evals_proofs: Vec<(Vec<F>, MerkleProof)> }  -> {"evals_proofs":[[[...],{"siblings":[...]}], ...]}
+//   FriQueryStep { evals, merkle_proof }, FriQueryRound { initial_trees_proof, steps },
+//   FriProof { commit_phase_merkle_caps, query_round_proofs, final_poly, pow_witness }
+// serde_json::to_string is compact (no whitespace), fields in declaration order.  Host-only code: needs no device.
+#include "../../include/zkm_b200.h"
+#include "dev.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <string>
+
+namespace zkm {
+namespace {
+
+struct Rd {
+    const u64* p; size_t n, pos = 0;
+    u64 u() { if (pos >= n) throw std::runtime_error("proof buffer truncated"); return p[pos++]; }
+    const u64* words(size_t k) { if (pos + k > n) throw std::runtime_error("proof buffer truncated"); const u64* r = p + pos; pos += k; return r; }
+};
+struct Js {
+    std::string s;
+    void num(u64 x) { char b[24]; int k = snprintf(b, sizeof b, "%llu", (unsigned long long)x); s.append(b, k); }
+    void ext(const u64* w) { s += '['; num(w[0]); s += ','; num(w[1]); s += ']'; }
+    void hash(const u64* w) { s += "{\"elements\":["; for (int i = 0; i < 4; i++) { if (i) s += ','; num(w[i]); } s += "]}"; }
+    template <class F> void list(size_t n, F item) { s += '['; for (size_t i = 0; i < n; i++) { if (i) s += ','; item(i); } s += ']'; }
+    void fs(const u64* w, size_t n) { list(n, [&](size_t i) { num(w[i]); }); }
+    void exts(const u64* w, size_t n) { list(n, [&](size_t i) { ext(w + 2 * i); }); }
+    void hashes(const u64* w, size_t n) { list(n, [&](size_t i) { hash(w + 4 * i); }); }
+    void key(const char* k) { s += '"'; s += k; s += "\":"; }
+};
+
+// positions the reader at the StarkProofWithMetadata of `table` and returns the header fields
+struct Header { size_t num_tables; std::vector<u64> pv; };
+static const u64 MAGIC = 0x464F4F52504D4B5AULL;
+
+void skip_table(Rd& r) {
+    r.words(12);
+    for (int c = 0; c < 3; c++) { size_t k = r.u(); r.words(4 * k); }
+    for (int v = 0; v < 4; v++) { size_t k = r.u(); r.words(2 * k); }
+    { size_t k = r.u(); r.words(k); }
+    { size_t k = r.u(); r.words(2 * k); }
+    size_t ncaps = r.u();
+    for (size_t i = 0; i < ncaps; i++) { size_t k = r.u(); r.words(4 * k); }
+    size_t nq = r.u();
+    for (size_t q = 0; q < nq; q++) {
+        size_t no = r.u();
+        for (size_t o = 0; o < no; o++) { size_t k = r.u(); r.words(k); k = r.u(); r.words(4 * k); }
+        size_t ns = r.u();
+        for (size_t st = 0; st < ns; st++) { size_t k = r.u(); r.words(2 * k); k = r.u(); r.words(4 * k); }
+    }
+    { size_t k = r.u(); r.words(2 * k); }
+    r.u();
+}
+
+void vec_field(Rd& r, Js& j, const char* name, int unit) {
+    j.key(name);
+    size_t k = r.u();
+    const u64* w = r.words(k * unit);
+    if (unit == 1) j.fs(w, k); else if (unit == 2) j.exts(w, k); else j.hashes(w, k);
+}
+
+void stark_proof_json(Rd& r, Js& j) {
+    r.words(12);                                            // init_challenger_state: metadata, not part of StarkProof
+    j.s += '{';
+    vec_field(r, j, "trace_cap", 4); j.s += ',';
+    vec_field(r, j, "auxiliary_polys_cap", 4); j.s += ',';
+    vec_field(r, j, "quotient_polys_cap", 4); j.s += ',';
+    j.key("openings"); j.s += '{';
+    vec_field(r, j, "local_values", 2); j.s += ',';
+    vec_field(r, j, "next_values", 2); j.s += ',';
+    vec_field(r, j, "auxiliary_polys", 2); j.s += ',';
+    vec_field(r, j, "auxiliary_polys_next", 2); j.s += ',';
+    vec_field(r, j, "ctl_zs_first", 1); j.s += ',';
+    vec_field(r, j, "quotient_polys", 2);
+    j.s += "},";
+    j.key("opening_proof"); j.s += '{';
+    j.key("commit_phase_merkle_caps");
+    size_t ncaps = r.u();
+    j.list(ncaps, [&](size_t) { size_t k = r.u(); j.hashes(r.words(4 * k), k); });
+    j.s += ',';
+    j.key("query_round_proofs");
+    size_t nq = r.u();
+    j.list(nq, [&](size_t) {
+        j.s += '{';
+        j.key("initial_trees_proof"); j.s += "{\"evals_proofs\":";
+        size_t no = r.u();
+        j.list(no, [&](size_t) {
+            j.s += '[';
+            size_t k = r.u(); j.fs(r.words(k), k);
+            j.s += ",{\"siblings\":";
+            k = r.u(); j.hashes(r.words(4 * k), k);
+            j.s += "}]";
+        });
+        j.s += "},";
+        j.key("steps");
+        size_t ns = r.u();
+        j.list(ns, [&](size_t) {
+            j.s += "{\"evals\":";
+            size_t k = r.u(); j.exts(r.words(2 * k), k);
+            j.s += ",\"merkle_proof\":{\"siblings\":";
+            k = r.u(); j.hashes(r.words(4 * k), k);
+            j.s += "}}";
+        });
+        j.s += '}';
+    });
+    j.s += ',';
+    j.key("final_poly"); j.s += "{\"coeffs\":";
+    { size_t k = r.u(); j.exts(r.words(2 * k), k); }
+    j.s += "},";
+    j.key("pow_witness"); j.num(r.u());
+    j.s += "}}";
+}
+
+char* dup(const std::string& s) {
+    char* m = (char*)malloc(s.size() + 1);
+    if (!m) throw std::runtime_error("out of host memory");
+    memcpy(m, s.c_str(), s.size() + 1);
+    return m;
+}
+int fail(char** err, const std::exception& e) {
+    if (err) { const char* w = e.what(); size_t n = strlen(w); char* m = (char*)malloc(n + 1); if (m) memcpy(m, w, n + 1); *err = m; }
+    return -1;
+}
+// reads the header up to the first table; returns num_tables and leaves the public values in the Js if asked
+size_t read_header(Rd& r, Js* pv) {
+    if (r.u() != MAGIC) throw std::runtime_error("bad proof magic");
+    if (r.u() != 1) throw std::runtime_error("bad proof version");
+    size_t nt = r.u();
+    size_t nch = r.u();
+    r.words(2 * nch);
+    const u64* rb = r.words(8);
+    const u64* ra = r.words(8);
+    size_t nu = r.u();
+    const u64* ud = r.words(nu);
+    if (pv) {
+        pv->s += "{\"roots_before\":{\"root\":"; pv->fs(rb, 8);
+        pv->s += "},\"roots_after\":{\"root\":"; pv->fs(ra, 8);
+        pv->s += "},\"userdata\":"; pv->fs(ud, nu); pv->s += '}';
+    }
+    return nt;
+}
+
+}  // namespace
+}  // namespace zkm
+
+using namespace zkm;
+extern "C" {
+
+int zkm_b200_proof_table_json(const uint64_t* proof, size_t proof_words, uint32_t table, char** json_out, size_t* json_len, char** err) {
+    if (err) *err = nullptr;
+    try {
+        ZKM_CHECK(proof && json_out, "null argument");
+        Rd r{proof, proof_words};
+        size_t nt = read_header(r, nullptr);
+        ZKM_CHECK(table < nt, "table index out of range");
+        for (uint32_t t = 0; t < table; t++) skip_table(r);
+        Js j;
+        j.s.reserve(1 << 20);
+        stark_proof_json(r, j);
+        if (json_len) *json_len = j.s.size();
+        *json_out = dup(j.s);
+    } catch (const std::exception& e) { return fail(err, e); }
+    return 0;
+}
+
+int zkm_b200_public_values_json(const uint64_t* proof, size_t proof_words, char** json_out, size_t* json_len, char** err) {
+    if (err) *err = nullptr;
+    try {
+        ZKM_CHECK(proof && json_out, "null argument");
+        Rd r{proof, proof_words};
+        Js j;
+        read_header(r, &j);
+        if (json_len) *json_len = j.s.size();
+        *json_out = dup(j.s);
+    } catch (const std::exception& e) { return fail(err, e); }
+    return 0;
+}
+
+}  // extern "C"

@@ -36,7 +36,7 @@ EXPORTS = [
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
 ]
 
 
@@ -97,6 +97,8 @@ def load():
     lib.zkm_b200_profile_families.restype = C.c_void_p
     lib.zkm_b200_layout_check.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkm_b200_layout_describe.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_proof_table_json.argtypes = [u64p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    lib.zkm_b200_public_values_json.argtypes = [u64p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
     lib.zkm_b200_timing_enable.argtypes = [C.c_int]
     lib.zkm_b200_last_timing.restype = C.c_void_p
     del errp
@@ -303,3 +305,22 @@ def synth_traces(lib, system_id, log_heights, seed=0x5EED000000000000):
         check(lib, lib.zkm_b200_synth_trace(system_id, t, lg, seed | (t << 16), u64ptr(a), C.byref(err)), err)
         out.append(a)
     return out
+
+
+def proof_table_json(lib, proof: np.ndarray, table: int) -> str:
+    """serde_json::to_string(&all_proof.stark_proofs[table].proof) of the reference (include/zkm_b200.h "proof wire format")."""
+    proof = np.ascontiguousarray(proof, dtype=np.uint64)
+    out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+    check(lib, lib.zkm_b200_proof_table_json(u64ptr(proof), proof.size, table, C.byref(out), C.byref(n), C.byref(err)), err)
+    s = C.string_at(out, n.value).decode()
+    lib.zkm_b200_free_string(out)
+    return s
+
+
+def public_values_json(lib, proof: np.ndarray) -> str:
+    proof = np.ascontiguousarray(proof, dtype=np.uint64)
+    out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+    check(lib, lib.zkm_b200_public_values_json(u64ptr(proof), proof.size, C.byref(out), C.byref(n), C.byref(err)), err)
+    s = C.string_at(out, n.value).decode()
+    lib.zkm_b200_free_string(out)
+    return s

@@ -165,6 +165,26 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table
                                    size_t n_memory_ops, const uint32_t roots_before[8], const uint32_t roots_after[8],
                                    const uint8_t* userdata, uint32_t userdata_len, const zkm_stark_config_t* cfg,
                                    uint64_t** proof_out, size_t* proof_words, char** err);
+/* Tables generated on the device from their operation logs (the per-table generators that
+ * Traces::into_tables runs on the CPU, witness/traces.rs:271-301).  Log formats, one entry per operation, u64 words:
+ *   Memory   (table 11)  7 words: context, segment, virt, timestamp, is_read, value, filter      -> MemoryStark::generate_trace
+ *   Logic    (table 10)  3 words: operator (0 AND, 1 OR, 2 XOR, 3 NOR), input0, input1 (u32)     -> LogicStark::generate_trace (logic.rs:108-183)
+ *   Poseidon (table 2)  13 words: the 12 input elements (canonical), timestamp                   -> PoseidonStark::generate_trace
+ *                                                                                                   (poseidon_stark.rs:51-145)
+ * Heights follow the reference: next power of two of max(number of operations, min_rows), min_rows = max(2^cap_height, 64).
+ * zkm_b200_table_from_ops returns the finished columns (column-major, malloc'ed; zkm_b200_free); zkm_b200_prove_with_ops is
+ * prove_with_trace_rows where every table t with op_logs[t].ops != NULL is generated on the device instead of being read from
+ * tables[t] / row_tables[t] -- only the log crosses PCIe (Logic: 24 B instead of 552 B per row). */
+typedef struct {
+    const uint64_t* ops;
+    size_t n_ops;
+} zkm_op_log_t;
+int zkm_b200_table_from_ops(uint32_t table, const uint64_t* ops, size_t n_ops, uint32_t min_rows, uint64_t** cols_out,
+                            uint32_t* log_n_out, char** err);
+int zkm_b200_prove_with_ops(const zkm_table_t tables[12], const zkm_table_rows_t* row_tables, const zkm_op_log_t op_logs[12],
+                            const uint32_t roots_before[8], const uint32_t roots_after[8], const uint8_t* userdata,
+                            uint32_t userdata_len, const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
+                            char** err);
 /* Same prover over another System of tables (zkm_b200/csrc/tables/systems.h: 0 = AllStark, 1 = Logic,
  * 2 = Poseidon+Logic+Memory, 3 = Poseidon, 4 = Memory, 5 = Arithmetic, 6 = Keccak+KeccakSponge+Logic+Memory,
  * 7 = Poseidon+PoseidonSponge+Memory, 8 = ShaExtend+ShaExtendSponge+Logic+Memory, 9 = ShaCompress+ShaCompressSponge+

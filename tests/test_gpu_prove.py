@@ -284,3 +284,90 @@ def test_memory_table_generated_on_the_device(zkm, orc):
     # one call: the table is generated on the device and stays there
     direct = zl.prove_with_memory_ops(zkm, traces, np.array(cpu.mem_ops, dtype=np.uint64))
     assert _first_diff(direct, proof) is None
+
+
+def test_timing_scopes_use_the_reference_names(zkm, orc):
+    """zkm_b200_last_timing: device-time scopes keyed by the reference's TimingTree strings (prover.rs:146,152,204,250-411,513,
+    545,578,620), nested like the reference's."""
+    traces = tr.all_stark_valid_traces(orc)
+    zkm.zkm_b200_timing_enable(1)
+    try:
+        zl.prove_with_traces(zkm, traces)
+        p = zkm.zkm_b200_last_timing()
+        text = C.string_at(p).decode()
+        zkm.zkm_b200_free_string(p)
+    finally:
+        zkm.zkm_b200_timing_enable(0)
+    rows = [ln.split("\t") for ln in text.splitlines()]
+    names = [r[2] for r in rows]
+    assert names[0] == "compute all trace commitments" and rows[0][0] == "0"
+    for t in ("Arithmetic", "Cpu", "Poseidon", "PoseidonSponge", "Keccak", "KeccakSponge", "ShaExtend", "ShaExtendSponge", "ShaCompress",
+              "ShaCompressSponge", "Logic", "Memory"):
+        assert f"compute trace commitment for {t}" in names
+    assert "compute all proofs given commitments" in names
+    for t in ("Arithmetic", "CPU", "Poseidon", "Poseidon sponge", "Keccak", "Keccak sponge", "SHA Extend", "SHA Extend sponge", "SHA Compress",
+              "SHA Compress sponge", "Logic", "Memory"):
+        assert f"prove {t} STARK" in names
+    i = names.index("prove CPU STARK")
+    inner = [n for r, n in zip(rows[i + 1:i + 7], names[i + 1:i + 7]) if r[0] == "2"]
+    assert inner == ["compute CTL data + lookup helper columns", "compute auxiliary polynomials commitment", "compute quotient polys",
+                     "compute quotient commitment", "compute openings", "compute openings proof"]
+    assert all(float(r[1]) >= 0 for r in rows) and sum(float(r[1]) for r in rows if r[0] == "0") > 0
+    # switched off again: the next proof records nothing
+    zl.prove_with_traces(zkm, traces)
+    p = zkm.zkm_b200_last_timing()
+    assert C.string_at(p) == b""
+    zkm.zkm_b200_free_string(p)
+
+
+def test_logic_and_poseidon_tables_generated_on_the_device(zkm, orc):
+    """zkm_b200_table_from_ops: the Logic table from (operator, input0, input1) logs and the Poseidon table from
+    (12 inputs, timestamp) logs equal the reference generators as restated in tests/traces.py (logic.rs:108-183) and in the
+    oracle (poseidon_stark.rs:51-145), including the padding rows and the minimum height."""
+    rng = np.random.default_rng(5)
+    for n_ops in (0, 1, 63, 64, 65, 1000, 5000):
+        ops = [(int(k), int(x), int(y)) for k, x, y in zip(rng.integers(0, 4, n_ops), rng.integers(0, 1 << 32, n_ops), rng.integers(0, 1 << 32, n_ops))]
+        if n_ops:
+            ops[0] = (3, 0xFFFFFFFF, 0)
+        arr = np.array(ops, dtype=np.uint64).reshape(n_ops, 3)
+        got = zl.table_from_ops(zkm, 10, arr)
+        n = max(64, 1 << max(0, (n_ops - 1).bit_length()))
+        assert got.shape == (69, n)
+        assert (got == tr.logic_trace_from_ops(ops, n.bit_length() - 1)).all()
+    with pytest.raises(zl.ZkmError, match="logic operation out of range"):
+        zl.table_from_ops(zkm, 10, np.array([[4, 1, 2]], dtype=np.uint64))
+    with pytest.raises(zl.ZkmError, match="no device-side generator"):
+        zl.table_from_ops(zkm, 4, np.zeros((1, 26), dtype=np.uint64))
+    from oracle.binding import u64ptr
+    for n_ops in (0, 3, 64, 200):
+        inputs = rng.integers(0, tr.P, size=(n_ops, 12), dtype=np.uint64)
+        if n_ops:
+            inputs[0] = tr.P - 1
+        ts = np.arange(7, 7 + n_ops, dtype=np.uint64)
+        got = zl.table_from_ops(zkm, 2, np.concatenate([inputs, ts[:, None]], axis=1).reshape(n_ops, 13))
+        n = max(64, 1 << max(0, (n_ops - 1).bit_length()))
+        full_in = np.zeros((n, 12), dtype=np.uint64); full_in[:n_ops] = inputs
+        full_ts = np.zeros(n, dtype=np.uint64); full_ts[:n_ops] = ts
+        rows = np.zeros((n, 262), dtype=np.uint64)
+        orc.orc_gen_poseidon_rows(u64ptr(full_in), u64ptr(full_ts), n, u64ptr(rows))
+        rows[n_ops:, 0] = 0                                   # padding rows: FILTER = 0 (poseidon_stark.rs:119-122)
+        assert got.shape == (262, n) and (got == rows.T).all()
+    with pytest.raises(zl.ZkmError, match="canonical"):
+        zl.table_from_ops(zkm, 2, np.full((1, 13), tr.P, dtype=np.uint64))
+
+
+def test_prove_with_ops_gives_the_same_proof(zkm, orc):
+    """zkm_b200_prove_with_ops: the Logic table enters as its operation log and is generated on the device inside the prove
+    call; the proof equals the proof over the host-built table (same 12-table valid trace as the drop-in test)."""
+    traces = tr.all_stark_valid_traces(orc)
+    logic = traces[10]
+    used = int(logic[:4].sum(axis=0).astype(bool).sum())
+    assert (logic[:4, :used].sum(axis=0) == 1).all() and not logic[:, used:].any()      # operations first, zero padding after
+    x = sum(logic[4 + i, :used].astype(np.uint64) << np.uint64(i) for i in range(32))
+    y = sum(logic[36 + i, :used].astype(np.uint64) << np.uint64(i) for i in range(32))
+    k = np.argmax(logic[:4, :used], axis=0).astype(np.uint64)
+    ops = np.stack([k, x, y], axis=1)
+    assert (zl.table_from_ops(zkm, 10, ops) == logic).all()
+    ref = zl.prove_with_traces(zkm, traces)
+    got = zl.prove_with_ops(zkm, traces, {10: ops})
+    assert _first_diff(got, ref) is None

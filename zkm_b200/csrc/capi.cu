@@ -201,26 +201,42 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
     ZKM_API_END
 }
 
+// One table built on the device from its operation log; returns the table height.
+static size_t table_from_ops_dev(int table, const u64* ops, size_t n_ops, size_t min_rows, DevBuf& cols, cudaStream_t s) {
+    switch (table) {
+        case tables::T_MEMORY: return memory_generate_trace_dev(ops, n_ops, cols, s);
+        case tables::T_LOGIC: return logic_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_POSEIDON: return poseidon_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        default: throw std::runtime_error(std::string("no device-side generator for table ") + tables::table_name(table) +
+                                          " (available: Logic, Poseidon, Memory)");
+    }
+}
+
 static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t num_tables, const uint64_t* const* d_tables,
                         const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
                         const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
-                        const zkm_table_rows_t* row_tables = nullptr, const uint64_t* mem_ops = nullptr, size_t n_mem_ops = 0) {
+                        const zkm_table_rows_t* row_tables = nullptr, const zkm_op_log_t* op_logs = nullptr) {
     Ctx& c = ctx();
     ZKM_CHECK(tables_in && roots_before && roots_after && cfg && proof_out && proof_words, "null argument");
     // tables given as rows (zkm_b200_prove_with_trace_rows): shape from the row descriptor, data uploaded as one block
     std::vector<zkm_table_t> merged(tables_in, tables_in + num_tables);
     for (uint32_t t = 0; t < num_tables && row_tables; t++)
         if (row_tables[t].rows) { merged[t].cols = nullptr; merged[t].ncols = row_tables[t].ncols; merged[t].log_n = row_tables[t].log_n; }
-    // the Memory table generated on the device from the operation log (zkm_b200_prove_with_memory_ops): never leaves HBM
+    // tables generated on the device from their operation logs (zkm_b200_prove_with_ops): they never leave HBM
     std::vector<char> generated(num_tables, 0);
-    DevBuf generated_memory;
-    if (mem_ops) {
-        ZKM_CHECK(system_id == tables::SYSTEM_ALL_STARK && !d_tables, "memory-operation logs are taken by the AllStark host entry points only");
-        size_t n = memory_generate_trace_dev(mem_ops, n_mem_ops, generated_memory, c.stream);
-        uint32_t lg = 0;
-        while (((size_t)1 << lg) < n) lg++;
-        merged[tables::T_MEMORY].cols = nullptr; merged[tables::T_MEMORY].ncols = 13; merged[tables::T_MEMORY].log_n = lg;
-        generated[tables::T_MEMORY] = 1;
+    std::vector<DevBuf> generated_bufs(num_tables);
+    if (op_logs) {
+        ZKM_CHECK(system_id == tables::SYSTEM_ALL_STARK && !d_tables, "operation logs are taken by the AllStark host entry points only");
+        // min_rows of Traces::into_tables (witness/traces.rs:239-240): max(number of cap elements, MIN_TRACE_LEN = 64)
+        const size_t min_rows = std::max<size_t>((size_t)1 << cfg->cap_height, 64);
+        for (uint32_t t = 0; t < num_tables; t++) {
+            if (!op_logs[t].ops) continue;
+            const size_t n = table_from_ops_dev((int)t, op_logs[t].ops, op_logs[t].n_ops, min_rows, generated_bufs[t], c.stream);
+            uint32_t lg = 0;
+            while (((size_t)1 << lg) < n) lg++;
+            merged[t].cols = nullptr; merged[t].ncols = (uint32_t)tables::table_num_columns((int)t); merged[t].log_n = lg;
+            generated[t] = 1;
+        }
     }
     const zkm_table_t* tables = merged.data();
     std::vector<DevBuf> row_staging(num_tables);
@@ -254,7 +270,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
             // pageable and, on this platform, also for pinned sources), so table t+1.. stream in while table t is
             // being committed; the prover waits on `ready` before touching a buffer
             const zkm_table_t* tb = &tables[t];
-            if (generated[t]) { in[t].values = std::move(generated_memory); continue; }      // already on the compute stream
+            if (generated[t]) { in[t].values = std::move(generated_bufs[t]); continue; }     // already on the compute stream
             const bool as_rows = row_tables && row_tables[t].rows;
             ZKM_CHECK((tb->cols || as_rows) && tb->ncols > 0, "null/empty table");
             if (!as_rows) for (uint32_t i = 0; i < tb->ncols; i++) ZKM_CHECK(tb->cols[i] != nullptr, "null column pointer");
@@ -426,8 +442,35 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t* tables, const zkm_table_ro
                                    uint64_t** proof_out, size_t* proof_words, char** err) {
     ZKM_API_BEGIN
     ZKM_CHECK(memory_ops, "null argument");
+    zkm_op_log_t logs[12] = {};
+    logs[tables::T_MEMORY].ops = memory_ops; logs[tables::T_MEMORY].n_ops = n_memory_ops;
     prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words,
-                 row_tables, memory_ops, n_memory_ops);
+                 row_tables, logs);
+    ZKM_API_END
+}
+int zkm_b200_prove_with_ops(const zkm_table_t* tables, const zkm_table_rows_t* row_tables, const zkm_op_log_t* op_logs,
+                            const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
+                            const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(op_logs, "null argument");
+    prove_common(tables::SYSTEM_ALL_STARK, tables, 12, nullptr, roots_before, roots_after, userdata, userdata_len, cfg, proof_out, proof_words,
+                 row_tables, op_logs);
+    ZKM_API_END
+}
+int zkm_b200_table_from_ops(uint32_t table, const uint64_t* ops, size_t n_ops, uint32_t min_rows, uint64_t** cols_out, uint32_t* log_n_out,
+                            char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK((ops || n_ops == 0) && cols_out && log_n_out, "null argument");
+    Ctx& c = ctx();
+    DevBuf cols;
+    const size_t n = table_from_ops_dev((int)table, ops, n_ops, min_rows, cols, c.stream);
+    const size_t words = (size_t)tables::table_num_columns((int)table) * n;
+    uint64_t* out = (uint64_t*)malloc(words * sizeof(u64));
+    ZKM_CHECK(out, "out of host memory");
+    cols.download(out, words);
+    uint32_t lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    *cols_out = out; *log_n_out = lg;
     ZKM_API_END
 }
 

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128, 8) merkle_level_kernel(const u64* __restr
 // single-thread permutation latency (~30 us, 11 such levels per 2^22-leaf tree and ~80 trees per proof).  Here 12 lanes
 // share one permutation, one state word each: the S-boxes of a full round run side by side and the MDS row of a lane is
 // 12 shuffled multiply-adds, so the dependent instruction chain is ~4x shorter.  Two permutations per warp (lanes 0-11
-// and 16-27).  Same merged partial-round constants as poseidon_permute_v8; outputs are bit-identical.
+// and 16-27).  Same merged partial-round constants as poseidon_permute_v9; outputs are bit-identical.
 __global__ void __launch_bounds__(128) merkle_level_coop_kernel(const u64* __restrict__ child, u64* __restrict__ parent, size_t n_parents,
                                                              QuarterMap qm) {
     const unsigned lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) merkle_level_coop_kernel(const u64* __res
             ah = p2_madw(__shfl_sync(0xffffffffu, hi, base + src), C[i], ah);
         }
         if (l == 0) { al = p2_madw(lo, 8u, al); ah = p2_madw(hi, 8u, ah); }
-        // value = al + ah * 2^32 (< 2^75), folded as in p2_mds
+        // value = al + ah * 2^32 (< 2^75), folded as in p9_recombine
         u32 al0 = (u32)al, al1 = (u32)(al >> 32), ah0 = (u32)ah, ah1 = (u32)(ah >> 32);
         u32 o0, o1;
         asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"

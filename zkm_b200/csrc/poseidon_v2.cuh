@@ -1,36 +1,17 @@
-// Device-tuned Goldilocks Poseidon permutation (same function as poseidon.cuh poseidon_permute; the
-// portable version stays for the host-side transcript).  Differences, all found by reading the SASS of
-// the portable version (tools/micro/poseidon_bench.cu):
-//  * 64x64->128 product as 4 IMAD.WIDE + one IADD3 carry chain, and the 2^64 = 2^32-1, 2^96 = -1
-//    reduction as a second carry chain (no ISETP/SEL pairs, no IMAD.X/IMAD.MOV on the FMA pipe);
-//  * the MDS row sums as explicit mad.wide.u32 accumulations (the compiler strength-reduces the small
-//    circulant constants into shift/add sequences on 64-bit values, 2.4x more instructions);
-//  * values stay non-canonical residues in [0, 2^64) until the end.
+// Device Goldilocks Poseidon permutation (same function as poseidon.cuh poseidon_permute, which stays as the portable
+// reference the micro-benchmark checks against).  What the SASS of the portable version led to, in order of effect
+// (profiles/r1_poseidon_variants_microbench.txt has every intermediate variant's throughput; the superseded code was removed):
+//  * the 128-bit product from the compiler's own 64x64 multiply (IMAD.WIDE.U32 with carry-out predicate + IMAD.WIDE.U32.X:
+//    4 IMAD + 2 IADD3, a form PTX cannot express), the 2^64 = 2^32 - 1 / 2^96 = -1 folding as one hand-written carry chain,
+//    values kept as lazy residues in [0, 2^64) until the end;
+//  * the MDS layer on the FP64 pipe, in the frequency domain of the length-12 cyclic convolution (below);
+//  * partial rounds in pairs, merged partial-round constants (tools/gen_poseidon_merged.py), one rolled round loop.
 #pragma once
 #include "poseidon.cuh"
 
 namespace zkm {
 #ifdef __CUDACC__
 
-// (a * b) mod p as a lazy residue in [0, 2^64)
-__device__ __forceinline__ u64 p2_mul(u64 a, u64 b) {
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    u32 o0, o1;
-    asm("{\n\t.reg .u64 p00,p01,p10,p11;\n\t.reg .u32 r0,r1,r2,r3,t1,u1,u2,v1,v2,w2,w3,s0,s1,t0,tt1,b,c,m;\n\t"
-        "mul.wide.u32 p00, %2, %4;\n\tmul.wide.u32 p01, %2, %5;\n\tmul.wide.u32 p10, %3, %4;\n\tmul.wide.u32 p11, %3, %5;\n\t"
-        "mov.b64 {r0, t1}, p00;\n\tmov.b64 {u1, u2}, p01;\n\tmov.b64 {v1, v2}, p10;\n\tmov.b64 {w2, w3}, p11;\n\t"
-        "add.cc.u32 r1, t1, u1;\n\taddc.cc.u32 r2, u2, w2;\n\taddc.u32 r3, w3, 0;\n\t"
-        "add.cc.u32 r1, r1, v1;\n\taddc.cc.u32 r2, r2, v2;\n\taddc.u32 r3, r3, 0;\n\t"
-        // reduce r3:r2:r1:r0 :  lo - (r2 + r3) + (r2 << 32), each wrap of 2^64 fixed with -/+ (2^32 - 1)
-        "add.cc.u32 s0, r2, r3;\n\taddc.u32 s1, 0, 0;\n\t"
-        "sub.cc.u32 t0, r0, s0;\n\tsubc.cc.u32 tt1, r1, s1;\n\tsubc.u32 b, 0, 0;\n\t"
-        "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
-        "add.cc.u32 tt1, tt1, r2;\n\taddc.u32 c, 0, 0;\n\t"
-        "sub.u32 m, 0, c;\n\t"
-        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
-        : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-    return (u64)o0 | ((u64)o1 << 32);
-}
 // a + c for a lazy residue a and a canonical constant c
 __device__ __forceinline__ u64 p2_add_canon(u64 a, u64 c) {
     u32 a0 = (u32)a, a1 = (u32)(a >> 32), c0 = (u32)c, c1 = (u32)(c >> 32);
@@ -42,166 +23,20 @@ __device__ __forceinline__ u64 p2_add_canon(u64 a, u64 c) {
         : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(c0), "r"(c1));
     return (u64)o0 | ((u64)o1 << 32);
 }
-__device__ __forceinline__ u64 p2_sbox7(u64 x) {
-    u64 x2 = p2_mul(x, x);
-    u64 x3 = p2_mul(x2, x);
-    u64 x4 = p2_mul(x2, x2);
-    return p2_mul(x3, x4);
-}
 __device__ __forceinline__ u64 p2_madw(u32 a, u32 c, u64 acc) {
     u64 r;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(c), "l"(acc));
     return r;
 }
-// out[r] = sum_i s[(i+r)%12] * CIRC[i] + (r == 0 ? 8 s[0] : 0)   (constants.rs:104-105)
-__device__ __forceinline__ void p2_mds(u64* s) {
-    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al = p2_madw(lo[(i + r) % 12], C[i], al);
-            ah = p2_madw(hi[(i + r) % 12], C[i], ah);
-        }
-        if (r == 0) { al = p2_madw(lo[0], 8u, al); ah = p2_madw(hi[0], 8u, ah); }
-        // value = al + ah * 2^32 < 2^75: (h : l1 : l0) with h = ah >> 32 + carry, reduce h*2^64 = h*(2^32-1)
-        u32 al0 = (u32)al, al1 = (u32)(al >> 32), ah0 = (u32)ah, ah1 = (u32)(ah >> 32);
-        u32 o0, o1;
-        asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
-            "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"            // (h : l1 : al0)
-            "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"  // h * (2^32 - 1) < 2^43
-            "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
-            "sub.u32 m, 0, cy;\n\t"
-            "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
-            : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
-        s[r] = (u64)o0 | ((u64)o1 << 32);
-    }
-}
-
-// ---- MDS on the FP64 pipe: the row sums  sum_i C[i] * (32-bit half)  are < 2^40, i.e. exact in double
-// arithmetic.  DFMA issues on its own pipe, so the 288 multiply-accumulates per layer stop competing with
-// the S-box integer work for the FMA/ALU pipes.  u32 <-> double conversions are the 2^52 magic-number
-// trick (one DADD each), never I2F/F2I.
+// u32 -> double by the 2^52 magic-number packing (one DADD); p9_cvt selects between this and I2F
 __device__ __forceinline__ double p3_u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
-__device__ __forceinline__ void p3_mds(u64* s) {
-    const double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
-    double lo[12], hi[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) { lo[i] = p3_u32_to_f64((u32)s[i]); hi[i] = p3_u32_to_f64((u32)(s[i] >> 32)); }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double al = lo[r] * C[0], ah = hi[r] * C[0];
-#pragma unroll
-        for (int i = 1; i < 12; i++) {
-            al = fma(lo[(i + r) % 12], C[i], al);
-            ah = fma(hi[(i + r) % 12], C[i], ah);
-        }
-        if (r == 0) { al = fma(lo[0], 8.0, al); ah = fma(hi[0], 8.0, ah); }
-        double tl = al + 4503599627370496.0, th = ah + 4503599627370496.0;
-        u32 al0 = (u32)__double2loint(tl), al1 = (u32)__double2hiint(tl) & 0xfffffu;
-        u32 ah0 = (u32)__double2loint(th), ah1 = (u32)__double2hiint(th) & 0xfffffu;
-        u32 o0, o1;
-        asm("{\n\t.reg .u32 l1,h,cy,m,e0,e1;\n\t.reg .u64 t;\n\t"
-            "add.cc.u32 l1, %3, %4;\n\taddc.u32 h, %5, 0;\n\t"
-            "mul.wide.u32 t, h, 0xffffffff;\n\tmov.b64 {e0, e1}, t;\n\t"
-            "add.cc.u32 e0, e0, %2;\n\taddc.cc.u32 e1, e1, l1;\n\taddc.u32 cy, 0, 0;\n\t"
-            "sub.u32 m, 0, cy;\n\t"
-            "add.cc.u32 %0, e0, m;\n\taddc.u32 %1, e1, 0;\n\t}"
-            : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
-        s[r] = (u64)o0 | ((u64)o1 << 32);
-    }
-}
-__device__ __forceinline__ void poseidon_permute_v3(u64* s) {
-    int rc = 0;
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
-        rc += 12;
-        p3_mds(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
-        rc += 12;
-        s[0] = p2_sbox7(s[0]);
-        p3_mds(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
-        rc += 12;
-        p3_mds(s);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
-}
-
-// ---- compact-code variants: the fully unrolled permutation is ~70 KB of SASS and the kernels built on it
-// stall on instruction fetch (ncu: "no instruction" is the top stall reason).  v4 keeps ONE copy of the MDS
-// and S-box code in a single 30-iteration round loop; v5 additionally shares the S-box code through a
-// non-inlined 4-wide helper.
-__device__ __forceinline__ void poseidon_permute_v4(u64* s) {
-    int rc = 0;
-#pragma unroll 1
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
-        rc += 12;
-        s[0] = p2_sbox7(s[0]);
-        if (full) {
-#pragma unroll
-            for (int i = 1; i < 12; i++) s[i] = p2_sbox7(s[i]);
-        }
-        p3_mds(s);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
-}
-// v6: the 12-wide S-box layer as a rolled loop of 3 x 4 with a register rotation (code ~370 instead of ~880
-// instructions): 0.904 G perm/s.  (Rolling the MDS the same way, or sharing the S-box through a non-inlined
-// helper, measured slower: 0.71 / 0.86.)
-__device__ __forceinline__ void p6_sbox_layer(u64* s) {
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) {
-        u64 a = p2_sbox7(s[0]), b = p2_sbox7(s[1]), c = p2_sbox7(s[2]), d = p2_sbox7(s[3]);
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-        s[8] = a; s[9] = b; s[10] = c; s[11] = d;
-    }
-}
-// v8 = v6 + merged partial-round constants.  In a partial round only element 0 passes the S-box, so the
-// constants of elements 1..11 commute with the (linear) MDS layer: writing the state as u + k with k a
-// data-independent vector, k_{r+1} = M * (0, (k_r + c_r)[1..11]), only a_r = (k_r + c_r)[0] has to be added
-// (to element 0, before its S-box), and the residue k_26 is folded into the constants of full round 26.
-// 22 additions instead of 264 per permutation; identical outputs (derivation + check: tools/gen_poseidon_merged.py).
+// Merged partial-round constants.  In a partial round only element 0 passes the S-box, so the constants of elements 1..11
+// commute with the (linear) MDS layer: writing the state as u + k with k a data-independent vector, k_{r+1} = M * (0, (k_r +
+// c_r)[1..11]), only a_r = (k_r + c_r)[0] has to be added (to element 0, before its S-box), and the residue k_26 is folded
+// into the constants of full round 26.  22 additions instead of 264 per permutation; identical outputs (derivation + check:
+// tools/gen_poseidon_merged.py).
 static __device__ __constant__ const u64 D_POSEIDON_PARTIAL_A[22] = {0x3cc3f892184df408ULL, 0x6754826bf0555feaULL, 0x07f136d86fe52ec6ULL, 0xcc31104c136e624cULL, 0xe75f601068e70acaULL, 0x27bb558ab181ed5eULL, 0xe0593bc645a018abULL, 0xa7ef236c2c5f0e1fULL, 0x2f2ed40f0e211d79ULL, 0x65b0ab09bec15af9ULL, 0x28f0f3bb03d3d776ULL, 0xb60fb82205a86176ULL, 0x6685ae6e5db8023dULL, 0x9b2390b07020a27cULL, 0xc3607e7232b11cefULL, 0xf618ae7058499e24ULL, 0xc18226dd334780c2ULL, 0xb57bff1387506176ULL, 0xec2475152d5a08ffULL, 0x04df43ffd0b458ffULL, 0x10f46236adcc3e98ULL, 0x52588ae3575e2ce9ULL};
 static __device__ __constant__ const u64 D_POSEIDON_RC26_MERGED[12] = {0x5405cc09b3ff0c06ULL, 0xe14dc071ace29846ULL, 0xbb56729c7877aa9eULL, 0x474fb5726a0068f3ULL, 0x2629b158383529bfULL, 0xe1cabee6fa7a9532ULL, 0xced9e7d28e6a6de9ULL, 0xd0fd98f1e129850fULL, 0x9689ab45a6d09dd7ULL, 0xba9673a4862f9848ULL, 0xa5c3a8c0fcbdbd41ULL, 0x8f4411a1226beb35ULL};
-__device__ __forceinline__ void poseidon_permute_v8(u64* s) {
-#pragma unroll 1
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-        if (full) {
-            const u64* rc = (r == 26) ? D_POSEIDON_RC26_MERGED : (D_POSEIDON_RC + 12 * r);
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], rc[i]);
-            p6_sbox_layer(s);
-        } else {
-            s[0] = p2_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 4]));
-        }
-        p3_mds(s);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
-}
-
 // ---- v9: fewer instructions per permutation (the kernels are issue-slot bound, ncu: profiles/r1_*):
 //  (a) the 128-bit product comes from the compiler's own 64x64 multiply (IMAD.WIDE.U32 with carry-out predicate +
 //      IMAD.WIDE.U32.X carry-in: 4 IMAD + 2 IADD3, not reachable from PTX mad/add.cc), the 2^64 = 2^32-1 / 2^96 = -1
@@ -299,7 +134,17 @@ __device__ __forceinline__ u64 p9_recombine(double al, double ah) {
         : "=r"(o0), "=r"(o1) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1));
     return (u64)o0 | ((u64)o1 << 32);
 }
+// The 12 S-boxes of a full round.  Rolled as 3 x 4 with a register rotation (one copy of four S-boxes in the instruction
+// cache: measured faster than straight-line code when the MDS was the integer version); ZKM_P9_SBOX_UNROLL=1 emits the 12
+// S-boxes straight-line (A/B knob, tools/micro/poseidon_bench.cu).
+#ifndef ZKM_P9_SBOX_UNROLL
+#define ZKM_P9_SBOX_UNROLL 0
+#endif
 __device__ __forceinline__ void p9_sbox_layer(u64* s) {
+#if ZKM_P9_SBOX_UNROLL
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = p9_sbox7(s[i]);
+#else
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
         u64 a = p9_sbox7(s[0]), b = p9_sbox7(s[1]), c = p9_sbox7(s[2]), d = p9_sbox7(s[3]);
@@ -307,98 +152,66 @@ __device__ __forceinline__ void p9_sbox_layer(u64* s) {
         for (int i = 0; i < 8; i++) s[i] = s[i + 4];
         s[8] = a; s[9] = b; s[10] = c; s[11] = d;
     }
+#endif
+}
+// One of the 19 steps of the permutation: 4 full rounds, 11 PAIRS of partial rounds, 4 full rounds (merged partial-round
+// constants).  In a pair only element 0 is brought back to a 64-bit residue between the two MDS layers.
+template <bool PAIR, int CV>
+__device__ __forceinline__ void p9_step(u64* s, int st) {
+    const bool full = (st < 4) || (st >= 15);
+    double lo[12], hi[12];
+    if (full) {
+        const int r = st < 4 ? st : st + 11;
+        const u64* rc = (r == 26) ? D_POSEIDON_RC26_MERGED : (D_POSEIDON_RC + 12 * r);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], rc[i]);
+        p9_sbox_layer(s);
+#pragma unroll
+        for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
+    } else {
+        const int r = 4 + 2 * (st - 4);
+        s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 4]));
+        double xl[12], xh[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) { xl[i] = p9_cvt<CV>((u32)s[i]); xh[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
+        p9_mds_half(xl, lo);
+        p9_mds_half(xh, hi);
+        if (PAIR) {
+            u64 s0 = p9_sbox7(p2_add_canon(p9_recombine<CV>(lo[0], hi[0]), D_POSEIDON_PARTIAL_A[r - 3]));
+            lo[0] = p9_cvt<CV>((u32)s0); hi[0] = p9_cvt<CV>((u32)(s0 >> 32));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(lo[i], hi[i]);
+            s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 3]));
+#pragma unroll
+            for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
+        }
+    }
+    double al[12], ah[12];
+    p9_mds_half(lo, al);
+    p9_mds_half(hi, ah);
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(al[i], ah[i]);
 }
 template <bool PAIR, int CV = 0>
 __device__ __forceinline__ void poseidon_permute_v9_t(u64* s) {
-    // 19 steps: 4 full rounds, 11 pairs of partial rounds, 4 full rounds (merged partial-round constants as in v8)
 #pragma unroll 1
-    for (int st = 0; st < 19; st++) {
-        const bool full = (st < 4) || (st >= 15);
-        double lo[12], hi[12];
-        if (full) {
-            const int r = st < 4 ? st : st + 11;
-            const u64* rc = (r == 26) ? D_POSEIDON_RC26_MERGED : (D_POSEIDON_RC + 12 * r);
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], rc[i]);
-            p9_sbox_layer(s);
-#pragma unroll
-            for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
-        } else {
-            const int r = 4 + 2 * (st - 4);
-            s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 4]));
-            double xl[12], xh[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) { xl[i] = p9_cvt<CV>((u32)s[i]); xh[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
-            p9_mds_half(xl, lo);
-            p9_mds_half(xh, hi);
-            if (PAIR) {
-                u64 s0 = p9_sbox7(p2_add_canon(p9_recombine<CV>(lo[0], hi[0]), D_POSEIDON_PARTIAL_A[r - 3]));
-                lo[0] = p9_cvt<CV>((u32)s0); hi[0] = p9_cvt<CV>((u32)(s0 >> 32));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(lo[i], hi[i]);
-                s[0] = p9_sbox7(p2_add_canon(s[0], D_POSEIDON_PARTIAL_A[r - 3]));
-#pragma unroll
-                for (int i = 0; i < 12; i++) { lo[i] = p9_cvt<CV>((u32)s[i]); hi[i] = p9_cvt<CV>((u32)(s[i] >> 32)); }
-            }
-        }
-        double al[12], ah[12];
-        p9_mds_half(lo, al);
-        p9_mds_half(hi, ah);
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p9_recombine<CV>(al[i], ah[i]);
-    }
+    for (int st = 0; st < 19; st++) p9_step<PAIR, CV>(s, st);
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
+}
+// Two independent states advanced step by step in the same loop body, so that the scheduler can issue the S-box phase of one
+// (ALU / FMA pipes) next to the MDS phase of the other (FP64 / XU pipes).  Needs ~2x the registers (A/B knob).
+template <int CV = 3>
+__device__ __forceinline__ void poseidon_permute_v9_x2(u64* a, u64* b) {
+#pragma unroll 1
+    for (int st = 0; st < 19; st++) { p9_step<true, CV>(a, st); p9_step<true, CV>(b, st); }
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a[i] = lz_canon(a[i]); b[i] = lz_canon(b[i]); }
 }
 __device__ __forceinline__ void poseidon_permute_v9(u64* s) { poseidon_permute_v9_t<true, 3>(s); }
-// the permutation every product kernel calls (ZKM_POSEIDON_V8 selects the previous generation for A/B timing)
-#ifdef ZKM_POSEIDON_V8
-#define poseidon_permute_dev poseidon_permute_v8
-#else
+// the permutation every product kernel calls
 #define poseidon_permute_dev poseidon_permute_v9
-#endif
 
-__device__ __forceinline__ void poseidon_permute_v6(u64* s) {
-    int rc = 0;
-#pragma unroll 1
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
-        rc += 12;
-        if (full) p6_sbox_layer(s); else s[0] = p2_sbox7(s[0]);
-        p3_mds(s);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
-}
-__device__ __forceinline__ void poseidon_permute_v2(u64* s) {
-    int rc = 0;
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
-        rc += 12;
-        p2_mds(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_add_canon(s[i], D_POSEIDON_RC[rc + i]);
-        rc += 12;
-        s[0] = p2_sbox7(s[0]);
-        p2_mds(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = p2_sbox7(p2_add_canon(s[i], D_POSEIDON_RC[rc + i]));
-        rc += 12;
-        p2_mds(s);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = lz_canon(s[i]);
-}
 #endif
 }  // namespace zkm

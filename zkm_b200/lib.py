@@ -36,7 +36,7 @@ EXPORTS = [
     "zkm_b200_batch_open", "zkm_b200_ntt", "zkm_b200_poseidon_permute", "zkm_b200_transcript_permute",
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
-    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
+    "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
 ]
 
 
@@ -324,3 +324,56 @@ def public_values_json(lib, proof: np.ndarray) -> str:
     s = C.string_at(out, n.value).decode()
     lib.zkm_b200_free_string(out)
     return s
+
+
+class OpLog(C.Structure):
+    _fields_ = [("ops", C.POINTER(C.c_uint64)), ("n_ops", C.c_size_t)]
+
+
+NCOLS_ALL_STARK = [54, 259, 262, 110, 2431, 470, 78, 76, 224, 127, 69, 13]
+
+
+def table_from_ops(lib, table: int, ops, min_rows: int = 64):
+    """zkm_b200_table_from_ops: ops = (n_ops, words_per_op) uint64 -> (ncols, n) table generated on the device."""
+    a = np.ascontiguousarray(ops, dtype=np.uint64)
+    assert a.ndim == 2
+    out, lg, err = C.POINTER(C.c_uint64)(), C.c_uint32(), C.c_void_p()
+    lib.zkm_b200_table_from_ops.argtypes = [C.c_uint32, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint32, C.POINTER(C.POINTER(C.c_uint64)),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
+    check(lib, lib.zkm_b200_table_from_ops(table, a.ctypes.data_as(C.POINTER(C.c_uint64)), a.shape[0], min_rows, C.byref(out), C.byref(lg),
+                                           C.byref(err)), err)
+    n, nc = 1 << lg.value, NCOLS_ALL_STARK[table]
+    t = np.ctypeslib.as_array(out, shape=(nc * n,)).copy().reshape(nc, n)
+    lib.zkm_b200_free(out)
+    return t
+
+
+def prove_with_ops(lib, traces, op_logs, roots_before=None, roots_after=None, userdata=bytes(32), cfg=None):
+    """zkm_b200_prove_with_ops: traces[t] column-major (ignored for tables with a log), op_logs = {table: (n_ops, k) uint64}."""
+    cfg = cfg or standard_fast_config(lib)
+    keep, cols = [], []
+    for t, a in enumerate(traces):
+        if t in op_logs:
+            cols.append(Table(None, 0, 0))
+        else:
+            tb, k = make_table(np.ascontiguousarray(a, dtype=np.uint64))
+            keep.append(k)
+            cols.append(tb)
+    arr = (Table * 12)(*cols)
+    logs = (OpLog * 12)()
+    for t, ops in op_logs.items():
+        a = np.ascontiguousarray(ops, dtype=np.uint64)
+        keep.append(a)
+        logs[t].ops = a.ctypes.data_as(C.POINTER(C.c_uint64))
+        logs[t].n_ops = a.shape[0]
+    rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
+    ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
+    out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
+    lib.zkm_b200_prove_with_ops.argtypes = [C.POINTER(Table), C.c_void_p, C.POINTER(OpLog), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                            C.c_char_p, C.c_uint32, C.POINTER(StarkConfig), C.POINTER(C.POINTER(C.c_uint64)),
+                                            C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    rc = lib.zkm_b200_prove_with_ops(arr, None, logs, rb, ra, userdata, len(userdata), C.byref(cfg), C.byref(out), C.byref(words), C.byref(err))
+    check(lib, rc, err)
+    proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+    lib.zkm_b200_free(out)
+    return proof

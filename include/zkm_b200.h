@@ -167,6 +167,9 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table
                                    uint64_t** proof_out, size_t* proof_words, char** err);
 /* Tables generated on the device from their operation logs (the per-table generators that
  * Traces::into_tables runs on the CPU, witness/traces.rs:271-301).  Log formats, one entry per operation, u64 words:
+ *   Arithmetic (table 0) 3 words: operator (the IS_* column index 0..25 = BinaryOperator::row_filter, arithmetic/mod.rs:135-165),
+ *                                 input0, input1 (u32) as Operation::binary receives them       -> ArithmeticStark::generate_trace
+ *                                 (arithmetic_stark.rs:155-192: one or two rows per operation, range-check columns included)
  *   Memory   (table 11)  7 words: context, segment, virt, timestamp, is_read, value, filter      -> MemoryStark::generate_trace
  *   Logic    (table 10)  3 words: operator (0 AND, 1 OR, 2 XOR, 3 NOR), input0, input1 (u32)     -> LogicStark::generate_trace (logic.rs:108-183)
  *   Poseidon (table 2)  13 words: the 12 input elements (canonical), timestamp                   -> PoseidonStark::generate_trace
@@ -174,7 +177,7 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table
  * Heights follow the reference: next power of two of max(number of operations, min_rows), min_rows = max(2^cap_height, 64).
  * zkm_b200_table_from_ops returns the finished columns (column-major, malloc'ed; zkm_b200_free); zkm_b200_prove_with_ops is
  * prove_with_trace_rows where every table t with op_logs[t].ops != NULL is generated on the device instead of being read from
- * tables[t] / row_tables[t] -- only the log crosses PCIe (Logic: 24 B instead of 552 B per row). */
+ * tables[t] / row_tables[t] -- only the log crosses PCIe (Logic: 24 B instead of 552 B per row, Arithmetic: 24 B instead of 432 B). */
 typedef struct {
     const uint64_t* ops;
     size_t n_ops;

@@ -205,10 +205,11 @@ int zkm_b200_commit_values_device(const uint64_t* d_values, uint32_t ncols, uint
 static size_t table_from_ops_dev(int table, const u64* ops, size_t n_ops, size_t min_rows, DevBuf& cols, cudaStream_t s) {
     switch (table) {
         case tables::T_MEMORY: return memory_generate_trace_dev(ops, n_ops, cols, s);
+        case tables::T_ARITHMETIC: return arithmetic_generate_trace_dev(ops, n_ops, cols, s);
         case tables::T_LOGIC: return logic_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         case tables::T_POSEIDON: return poseidon_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         default: throw std::runtime_error(std::string("no device-side generator for table ") + tables::table_name(table) +
-                                          " (available: Logic, Poseidon, Memory)");
+                                          " (available: Arithmetic, Logic, Poseidon, Memory)");
     }
 }
 

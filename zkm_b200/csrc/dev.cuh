@@ -111,6 +111,7 @@ void arith_generate_range_checks(u64* cols, size_t n, int first_shared, int num_
 size_t memory_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevBuf& cols, cudaStream_t s);
 
 // Tables generated from operation logs (tracegen.cu): return the table height, fill ncols x height columns.
+size_t arithmetic_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevBuf& cols, cudaStream_t s);
 size_t logic_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 size_t poseidon_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 

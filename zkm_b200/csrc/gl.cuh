@@ -135,17 +135,19 @@ ZKM_HD gl operator*(gl a, gl b) {
     return gl(r >= GL_P ? r - GL_P : r);
 #elif defined(__CUDA_ARCH__) && ZKM_GLMUL == 4
     // as 3, with the final canonicalisation folded into the chain: x >= p  <=>  x_hi == 2^32 - 1 and x_lo != 0, and then
-    // x - p = (0 : x_lo - 1).  Two compares + two predicated moves (13 ALU-pipe + 9 FMA-pipe instructions per multiply in the
-    // SASS instead of 15 + 10).
+    // x - p = (0 : x_lo - 1): two compares + two predicated moves instead of a 64-bit subtract, compare and select.
+    // (A first version also took the carry mask with `subc` right after `add.cc`; mixing the add and subtract carry
+    // conventions gave wrong results on the device -- profiles/r2c_glmul4_note.txt -- so the mask is built as in 3.)
     unsigned __int128 pr = (unsigned __int128)a.v * b.v;
     u64 lo = (u64)pr, hi = (u64)(pr >> 64);
     u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32);
     u32 o0, o1;
-    asm("{\n\t.reg .u32 s0,s1,t0,tt1,b,m,x0,x1;\n\t.reg .pred p,q;\n\t"
+    asm("{\n\t.reg .u32 s0,s1,t0,tt1,b,c,m,x0,x1;\n\t.reg .pred p,q;\n\t"
         "add.cc.u32 s0, %4, %5;\n\taddc.u32 s1, 0, 0;\n\t"
         "sub.cc.u32 t0, %2, s0;\n\tsubc.cc.u32 tt1, %3, s1;\n\tsubc.u32 b, 0, 0;\n\t"
         "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
-        "add.cc.u32 tt1, tt1, %4;\n\tsubc.u32 m, 0, 0;\n\t"
+        "add.cc.u32 tt1, tt1, %4;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 m, 0, c;\n\t"
         "add.cc.u32 x0, t0, m;\n\taddc.u32 x1, tt1, 0;\n\t"
         "setp.ne.u32 p, x0, 0;\n\tsetp.eq.and.u32 q, x1, 0xffffffff, p;\n\t"
         "@q sub.u32 x0, x0, 1;\n\t@q mov.u32 x1, 0;\n\t"

@@ -425,6 +425,7 @@ def main():
     ap.add_argument("--workload", default="U20")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workers", type=int, default=0, help="proofs in flight per GPU (worker contexts); 0 = 3")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the e2e leg from pageable host memory")
     ap.add_argument("--no-in-segment", action="store_true", help="N > 1: skip the in-segment sharding measurement")
     ap.add_argument("--host-memory", default="pinned", choices=["pinned", "pageable"],
                     help="e2e leg: where the caller's trace columns live (the reference's Vec<F> columns are pageable)")
@@ -544,6 +545,14 @@ def main():
         sg.step_e2e_nogather = lambda sg=sg: sg.step_e2e(gather=False)
     t_e2e = timed_concurrent("step_e2e_nogather", 1, args.steps, after_join=gather_all)
     barrier()
+    # the same call from PAGEABLE host columns -- what the reference's caller holds (one Vec<F> per column) -- at N = 1
+    t_e2e_pageable, pageable_steps = None, 0
+    if world == 1 and args.host_memory == "pinned" and not args.no_pageable:
+        for sg in segs:
+            sg.prepare_host(pinned=False)
+        pageable_steps = min(args.steps, 3)
+        t_e2e_pageable = timed_concurrent("step_e2e_nogather", 1, pageable_steps)
+        barrier()
     for w in workers:
         w.close()
     # ---- latency of ONE proof on one GPU (one context, nothing else in flight) ----
@@ -618,7 +627,9 @@ def main():
                                           f"{NW * world} proofs)"},
                 "e2e": {"value": e2e, "unit": seg.unit, "ms_per_step": t_e2e / args.steps,
                         "h2d_bytes_per_step": seg.input_bytes * NW, "d2h_bytes_per_step": seg.output_bytes * NW,
-                        "host_memory": args.host_memory},
+                        "host_memory": args.host_memory,
+                        "pageable_host_memory": ({"value": pageable_steps * NW / (t_e2e_pageable * 1e-3), "unit": seg.unit, "steps": pageable_steps}
+                                                 if t_e2e_pageable else None)},
                 "gpu_launches": int(launches),
                 "roofline": roof(top[0], top[1], notes.get(top[0], "")),
                 "dominant_family": top[0],

@@ -81,11 +81,13 @@ ZKM_HD u64 gl_reduce96(u64 lo, u32 hi32) {
 }
 
 // ZKM_GLMUL selects the device multiply: 0 = PTX product + PTX folding, 1 = compiler product + 128-bit-sum folding,
-// 2 = compiler product + compare/select folding, 3 = compiler product + PTX folding.  The kernels built on this are bound by
+// 2 = compiler product + compare/select folding, 3 = compiler product + PTX folding, 4 = 3 with the canonicalisation done by
+// two compares + two predicated moves (the product build: NTT -3.8 %, quotient -3.8 %, openings -10 % against 3 on U20,
+// profiles/r2d_glmul_ab.txt).  The kernels built on this are bound by
 // the ALU pipe (IADD3/LOP3/SEL, ncu: 72-78 % vs 15 % on the FMA pipe), so what counts is how much of the carry handling the
 // compiler can place on the FMA pipe (IMAD.WIDE with carry-out, IMAD.X), not the instruction total.
 #ifndef ZKM_GLMUL
-#define ZKM_GLMUL 3
+#define ZKM_GLMUL 4
 #endif
 ZKM_HD gl operator*(gl a, gl b) {
 #if defined(__CUDA_ARCH__) && ZKM_GLMUL == 0

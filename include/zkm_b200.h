@@ -174,6 +174,8 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table
  *   Logic    (table 10)  3 words: operator (0 AND, 1 OR, 2 XOR, 3 NOR), input0, input1 (u32)     -> LogicStark::generate_trace (logic.rs:108-183)
  *   Poseidon (table 2)  13 words: the 12 input elements (canonical), timestamp                   -> PoseidonStark::generate_trace
  *                                                                                                   (poseidon_stark.rs:51-145)
+ *   Keccak   (table 4)  26 words: the 25 input lanes (input[y * 5 + x] = lane (x, y)), timestamp -> KeccakStark::generate_trace
+ *                                                                                                   (keccak_stark.rs:62-237, 24 rows per permutation)
  * Heights follow the reference: next power of two of max(number of operations, min_rows), min_rows = max(2^cap_height, 64).
  * zkm_b200_table_from_ops returns the finished columns (column-major, malloc'ed; zkm_b200_free); zkm_b200_prove_with_ops is
  * prove_with_trace_rows where every table t with op_logs[t].ops != NULL is generated on the device instead of being read from

@@ -394,3 +394,20 @@ def test_arithmetic_table_generated_on_the_device(zkm, orc):
     assert _first_diff(zl.prove_system(zkm, tr.SYSTEM_ARITH, [t]), zl.prove_system(zkm, tr.SYSTEM_ARITH, [tr.arithmetic_trace()])) is None
     with pytest.raises(zl.ZkmError, match="arithmetic operation out of range"):
         zl.table_from_ops(zkm, 0, np.array([[ag.IS_DIVU, 5, 0]], dtype=np.uint64))
+
+
+def test_keccak_table_generated_on_the_device(zkm, orc):
+    """zkm_b200_table_from_ops for the Keccak-f table (2431 columns, 24 rows per permutation) against tests/hash_gen.py (the
+    Python restatement of keccak_stark.rs:62-237, itself checked against hashlib's SHA3): every cell, the zero padding and
+    the minimum height; the generated table satisfies the transcribed constraints."""
+    import hash_gen as hg
+    rng = np.random.default_rng(9)
+    for perms in (0, 1, 2, 3, 11):
+        ins = [([int(v) for v in rng.integers(0, 1 << 64, size=25, dtype=np.uint64)], 10 + i) for i in range(perms)]
+        ops = np.array([list(i) + [ts] for i, ts in ins], dtype=np.uint64).reshape(perms, 26)
+        got = zl.table_from_ops(zkm, 4, ops)
+        n = max(64, 1 << max(0, (24 * perms - 1).bit_length()))
+        want = hg.keccak_trace(ins, n.bit_length() - 1)
+        assert got.shape == want.shape == (2431, n)
+        assert (got == want).all()
+    assert orc.orc_check_table_constraints(4, binding.col_ptrs(got), 2431, 9) == 0

@@ -208,8 +208,9 @@ static size_t table_from_ops_dev(int table, const u64* ops, size_t n_ops, size_t
         case tables::T_ARITHMETIC: return arithmetic_generate_trace_dev(ops, n_ops, cols, s);
         case tables::T_LOGIC: return logic_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         case tables::T_POSEIDON: return poseidon_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_KECCAK: return keccak_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         default: throw std::runtime_error(std::string("no device-side generator for table ") + tables::table_name(table) +
-                                          " (available: Arithmetic, Logic, Poseidon, Memory)");
+                                          " (available: Arithmetic, Poseidon, Keccak, Logic, Memory)");
     }
 }
 

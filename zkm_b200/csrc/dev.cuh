@@ -113,6 +113,7 @@ size_t memory_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevBuf& 
 // Tables generated from operation logs (tracegen.cu): return the table height, fill ncols x height columns.
 size_t arithmetic_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevBuf& cols, cudaStream_t s);
 size_t logic_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t keccak_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 size_t poseidon_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].

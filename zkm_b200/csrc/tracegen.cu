@@ -145,6 +145,95 @@ size_t poseidon_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_ro
 
 }  // namespace zkm
 
+// ----------------------------------------------------------------------------------------------------------- Keccak
+// reference keccak/keccak_stark.rs:62-237 KeccakStark::generate_trace_rows: 24 rows per permutation (one per round) holding the
+// round input lanes A as 32-bit limbs, the column parities C and C' and the theta output A' as bits, the chi output A'' as
+// limbs, the bits of A''[0][0] and the limbs of A''[0][0] ^ RC[round]; zero rows up to the next power of two of
+// max(24 * perms, min_rows).  Log entry = 26 words: the 25 input lanes (input[y * 5 + x] is lane (x, y)), timestamp.
+// A round needs the previous round's output, so one thread walks the 24 rounds of a permutation and writes 24 x 2431 cells
+// (a warp's stores to one column are 24 rows apart; the table is small in every real segment: 2^6..2^10 rows).
+#include "tables/keccak.h"
+namespace zkm {
+__global__ void __launch_bounds__(64) keccak_rows_kernel(const u64* __restrict__ ops, size_t n_perms, size_t n, u64* __restrict__ cols) {
+    namespace kc = tables::keccak;
+    using namespace tables::keccak;                      // ZKM_K(KECCAK_R), ZKM_K(KECCAK_RC)
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_perms) return;
+    u64 A[5][5];
+#pragma unroll
+    for (int x = 0; x < 5; x++)
+#pragma unroll
+        for (int y = 0; y < 5; y++) A[x][y] = ops[26 * p + y * 5 + x];
+    const u64 ts = ops[26 * p + 25];
+    auto rotl = [](u64 v, int r) { r &= 63; return r ? (v << r) | (v >> (64 - r)) : v; };
+#pragma unroll 1
+    for (int rnd = 0; rnd < kc::NUM_ROUNDS; rnd++) {
+        const size_t row = p * kc::NUM_ROUNDS + rnd;
+        auto put = [&](int c, u64 v) { cols[(size_t)c * n + row] = v; };
+        put(kc::reg_step(rnd), 1);
+        put(kc::TIMESTAMP, ts);
+        u64 C[5], Cp[5];
+#pragma unroll
+        for (int x = 0; x < 5; x++) {
+            C[x] = A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4];
+#pragma unroll
+            for (int y = 0; y < 5; y++) { put(kc::reg_a(x, y), A[x][y] & 0xFFFFFFFFull); put(kc::reg_a(x, y) + 1, A[x][y] >> 32); }
+        }
+#pragma unroll
+        for (int x = 0; x < 5; x++) Cp[x] = C[x] ^ C[(x + 4) % 5] ^ rotl(C[(x + 1) % 5], 1);
+        u64 Ap[5][5];
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+#pragma unroll
+            for (int y = 0; y < 5; y++) Ap[x][y] = A[x][y] ^ C[x] ^ Cp[x];
+#pragma unroll 1
+        for (int z = 0; z < 64; z++) {
+#pragma unroll
+            for (int x = 0; x < 5; x++) {
+                put(kc::reg_c(x, z), (C[x] >> z) & 1);
+                put(kc::reg_c_prime(x, z), (Cp[x] >> z) & 1);
+#pragma unroll
+                for (int y = 0; y < 5; y++) put(kc::reg_a_prime(x, y, z), (Ap[x][y] >> z) & 1);
+            }
+        }
+        // B[x, y] = rot(A'[(x + 3y) % 5, x], R[(x + 3y) % 5][x])   (columns.rs:83-92);  A''[x, y] = B[x, y] ^ (~B[x+1, y] & B[x+2, y])
+        u64 B[5][5];
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+#pragma unroll
+            for (int y = 0; y < 5; y++) { const int a = (x + 3 * y) % 5; B[x][y] = rotl(Ap[a][x], (int)ZKM_K(KECCAK_R)[a * 5 + x]); }
+#pragma unroll
+        for (int x = 0; x < 5; x++)
+#pragma unroll
+            for (int y = 0; y < 5; y++) {
+                A[x][y] = B[x][y] ^ (~B[(x + 1) % 5][y] & B[(x + 2) % 5][y]);
+                put(kc::reg_a_prime_prime(x, y), A[x][y] & 0xFFFFFFFFull); put(kc::reg_a_prime_prime(x, y) + 1, A[x][y] >> 32);
+            }
+#pragma unroll 1
+        for (int z = 0; z < 64; z++) put(kc::reg_a_prime_prime_0_0_bit(z), (A[0][0] >> z) & 1);
+        A[0][0] ^= ZKM_K(KECCAK_RC)[rnd];
+        put(kc::REG_A_PRIME_PRIME_PRIME_0_0_LO, A[0][0] & 0xFFFFFFFFull);
+        put(kc::REG_A_PRIME_PRIME_PRIME_0_0_HI, A[0][0] >> 32);
+    }
+}
+
+size_t keccak_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, DevBuf& cols, cudaStream_t s) {
+    namespace kc = tables::keccak;
+    const size_t n = padded_rows(n_ops * kc::NUM_ROUNDS, min_rows);
+    ZKM_CHECK(n <= ((size_t)1 << 22), "too many Keccak permutations");
+    DevBuf ops(26 * n_ops + 1, s);
+    if (n_ops) ops.upload(h_ops, 26 * n_ops);
+    cols.alloc((size_t)kc::NUM_COLUMNS * n, s);
+    cols.zero();
+    ProfScope ps("keccak_trace", s, 208.0 * (double)n_ops + 8.0 * kc::NUM_COLUMNS * (double)n);
+    if (n_ops) {
+        keccak_rows_kernel<<<(unsigned)((n_ops + 63) / 64), 64, 0, s>>>(ops.p, n_ops, n, cols.p);
+        ZKM_LAUNCHED();
+    }
+    return n;
+}
+}  // namespace zkm
+
 // ------------------------------------------------------------------------------------------------------- Arithmetic
 // reference arithmetic/arithmetic_stark.rs:155-192 ArithmeticStark::generate_trace: every operation becomes one row, or two for
 // DIV / DIVU / SRL(V) / SRA(V) (mod.rs:237-312 binary_op_to_rows), rows are zero-padded to a power of two >= 2^16, then

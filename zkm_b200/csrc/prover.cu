@@ -123,6 +123,24 @@ static const char* reference_scope_name(int kind) {
 // `Table` Debug names (all_stark.rs:97-110), as in "compute trace commitment for {:?}" (prover.rs:152)
 static const char* reference_table_debug_name(int kind) { return tables::table_name(kind); }
 
+// StarkOpeningSet::new evaluations, column-sharded when the table is proved by a shard group (shard.cuh): rank r evaluates
+// columns [r * per, (r + 1) * per) and the (tiny) results are all-gathered, so every rank still observes all openings.
+static void eval_polys_sharded(bool sharded, const u64* d_coeffs, int ncols, int log_n, const gl2* pts, int npts, u64* h_out, cudaStream_t s) {
+    const Shard& sh = shard();
+    if (!sharded || !sh.active() || ncols < 2 * sh.world) { eval_polys_at_points(d_coeffs, ncols, log_n, pts, npts, h_out, s); return; }
+    const size_t n = (size_t)1 << log_n;
+    const int per = (ncols + sh.world - 1) / sh.world;
+    const int c0 = std::min(ncols, sh.rank * per), c1 = std::min(ncols, c0 + per);
+    const size_t words = (size_t)per * npts * 2;
+    std::vector<u64> mine(words, 0), all(words * sh.world);
+    if (c1 > c0) eval_polys_at_points(d_coeffs + (size_t)c0 * n, c1 - c0, log_n, pts, npts, mine.data(), s);
+    DevBuf send(words, s), recv(words * sh.world, s);
+    send.upload(mine.data(), words);
+    shard_all_gather(send.p, recv.p, words, s);
+    recv.download(all.data(), all.size());
+    memcpy(h_out, all.data(), (size_t)ncols * npts * 2 * sizeof(u64));      // rank slices are contiguous in column order
+}
+
 static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChallenges& ctl_ch, HostChallenger& ch, ProofWriter& W) {
     Ctx& c = ctx();
     cudaStream_t s = c.stream;
@@ -193,12 +211,12 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
         TimedScope ts("compute openings", s);                          // StarkOpeningSet::new (prover.rs:601; untimed upstream)
         gl2 pts[3] = {zeta, zeta_next, gl2::one()};
         std::vector<u64> h((size_t)std::max(std::max(C, naux), Q) * 3 * 2);
-        eval_polys_at_points(job.trace.coeffs.p, C, log_n, pts, 2, h.data(), s);
+        eval_polys_sharded(job.trace.sharded, job.trace.coeffs.p, C, log_n, pts, 2, h.data(), s);
         for (int i = 0; i < C; i++) {
             local_values[i] = gl2(gl(h[(i * 2 + 0) * 2]), gl(h[(i * 2 + 0) * 2 + 1]));
             next_values[i] = gl2(gl(h[(i * 2 + 1) * 2]), gl(h[(i * 2 + 1) * 2 + 1]));
         }
-        eval_polys_at_points(aux.coeffs.p, naux, log_n, pts, 3, h.data(), s);
+        eval_polys_sharded(job.trace.sharded, aux.coeffs.p, naux, log_n, pts, 3, h.data(), s);
         for (int i = 0; i < naux; i++) {
             aux_local[i] = gl2(gl(h[(i * 3 + 0) * 2]), gl(h[(i * 3 + 0) * 2 + 1]));
             aux_next[i] = gl2(gl(h[(i * 3 + 1) * 2]), gl(h[(i * 3 + 1) * 2 + 1]));

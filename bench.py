@@ -558,7 +558,7 @@ def main():
     # ---- latency of ONE proof on one GPU (one context, nothing else in flight) ----
     barrier()
     t_single = seg.timed(lambda: [seg.step_device() for _ in range(args.steps)]) / args.steps
-    # ---- in-segment sharding (north_star): groups of min(N, 4) GPUs prove ONE segment together ----
+    # ---- in-segment sharding (north_star): all N (<= 8) GPUs prove ONE segment together ----
     in_segment = None
     if world > 1 and not args.no_in_segment:
         import hashlib

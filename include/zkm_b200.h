@@ -70,11 +70,11 @@ int zkm_b200_worker_bind(zkm_worker_t* w, char** err);      /* NULL: back to the
 void zkm_b200_worker_destroy(zkm_worker_t* w);
 
 /* In-segment sharding (BASELINE north_star: "partition independent trace-table NTTs and Merkle subtrees
- * across the GPUs ... NCCL only for the final cap/root gather").  world = 2 or 4 processes, one per GPU, form a group: after
+ * across the GPUs ... NCCL only for the final cap/root gather").  world = 2, 4 or 8 processes, one per GPU, form a group: after
  * zkm_b200_shard_init every prove call on the process-wide context is COOPERATIVE -- all ranks of the group must make the same
  * call with the same inputs, and every rank returns the same proof, bit-identical to the single-GPU proof.  Each rank computes
  * the coset transforms, leaf hashes and Merkle subtrees of the LDE cosets it owns (4/world of the 4 cosets = 16/world whole cap
- * subtrees) and its half of the quotient; the exchanges are the cap entries of every commitment (ncclAllGather, 512 B per
+ * subtrees; with 8 ranks two ranks share a coset's transform and hash one half of its leaves each) and its share of the quotient; the exchanges are the cap entries of every commitment (ncclAllGather, 512 B per
  * tree), the two halves of the quotient values (ncclBroadcast) and the opened rows/paths of the FRI queries (ncclAllGather).
  * Rank 0 obtains the 128-byte NCCL unique id and the caller distributes it (bench.py / zkm_b200/multi.py: torch.distributed
  * broadcast).  NCCL is bound at run time (libnccl.so.2); single-GPU use does not need it.  world = 1 leaves sharding off. */

@@ -1,4 +1,4 @@
-"""GPU test of in-segment sharding (include/zkm_b200.h "In-segment sharding"): G = 2 or 4 processes, one per
+"""GPU test of in-segment sharding (include/zkm_b200.h "In-segment sharding"): G = 2, 4 or 8 processes, one per
 GPU, prove ONE segment together through the C ABI; every rank's proof must be identical and equal to the proof the same
 library computes on one GPU alone (which tests/test_gpu_prove.py compares with the oracle word for word).  Needs >= 2 GPUs
 on the box (`gpurun --gpus 2`); skipped otherwise."""
@@ -46,7 +46,7 @@ def _worker(rank, world, port, heights, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_in_segment_sharded_proof_equals_single_gpu_proof(orc, world):
     import torch
     import torch.multiprocessing as mp

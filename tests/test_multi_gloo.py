@@ -149,11 +149,24 @@ def test_shard_ownership_rules():
     from zkm_b200 import multi
     assert multi.owned_cosets(0, 2) == [0, 1] and multi.owned_cosets(1, 2) == [2, 3]
     assert [multi.owned_cosets(r, 4) for r in range(4)] == [[0], [1], [2], [3]]
-    for g in (1, 2, 4):
+    assert [multi.owned_cosets(r, 8) for r in range(8)] == [[0], [0], [1], [1], [2], [2], [3], [3]]      # two ranks per coset
+    log_leaves = 9
+    for g in (1, 2, 4, 8):
         owned = sorted(sum((multi.owned_cap_entries(r, g) for r in range(g)), []))
         assert owned == list(range(16))                             # every cap entry has exactly one owner
         # the two halves of the quotient domain (LDE cosets 0 and 2) go to different ranks as soon as there are two
         assert (multi.coset_owner(0, g) != multi.coset_owner(2, g)) == (g > 1)
+        # a leaf's owner is the rank whose segments contain it, and its coset is one that rank computes
+        nseg = 4 * multi.parts(g)
+        for leaf in range(1 << log_leaves):
+            r = multi.leaf_owner(leaf, log_leaves, g)
+            assert (leaf * nseg) >> log_leaves in multi.owned_segments(r, g)
+            assert multi.bitrev(leaf, log_leaves) % 4 in multi.owned_cosets(r, g)
+        # 8 ranks: the two owners of a coset split its rows by parity (row i = natural LDE index >> 2)
+        if g == 8:
+            for leaf in range(1 << log_leaves):
+                i = multi.bitrev(leaf, log_leaves) >> 2
+                assert multi.leaf_owner(leaf, log_leaves, g) % 2 == i % 2
     with pytest.raises(ValueError):
         multi.owned_cosets(0, 3)
 

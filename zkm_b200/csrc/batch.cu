@@ -174,13 +174,14 @@ void ctx_shutdown() {
 // full by every rank).  The rule depends on the shape only, so every
 // rank takes the same branch.
 static bool commit_is_sharded(const Batch& b) {
-    return shard().active() && b.rate_bits == 2 && b.cap_height >= 2 && b.log_n >= 13;
+    return shard().active() && b.rate_bits == 2 && (int)b.cap_height >= shard().log_segs() && b.log_n >= 13;
 }
 static void commit_tree(Batch& b, cudaStream_t s) {
     const Shard& sh = shard();
     merkle_alloc(b.tree, b.lde_bits(), b.cap_height, s);
     b.tree.sharded = b.sharded;
-    if (b.sharded) lde_leaf_hash(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s, sh.coset_begin(), sh.coset_count());
+    if (b.sharded) lde_leaf_hash(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s, sh.coset_begin(), sh.coset_count(),
+                                 sh.log_parts(), sh.part());
     else lde_leaf_hash(b.lde.p, b.lde_n(), b.ncols, b.log_n, b.rate_bits, b.tree.digests.p, s);
     merkle_build_from_leaf_digests(b.tree, s);
 }

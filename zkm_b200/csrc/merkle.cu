@@ -21,8 +21,9 @@ __device__ __forceinline__ size_t lde_pos_of_leaf(u32 leaf, int log_n, int rate_
 }
 
 __global__ void __launch_bounds__(128, 8) lde_leaf_hash_kernel(const u64* __restrict__ lde, size_t cs, int ncols, int log_n,
-                                                            int rate_bits, u64* __restrict__ dig, size_t pos_begin, size_t pos_end) {
-    size_t pos = pos_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                            int rate_bits, u64* __restrict__ dig, size_t pos_begin, size_t pos_end, int row_log_stride,
+                                                            int row_offset) {
+    size_t pos = pos_begin + ((((size_t)blockIdx.x * blockDim.x + threadIdx.x) << row_log_stride) | row_offset);
     if (pos >= pos_end) return;
     // position -> natural index -> leaf index
     u32 j = (u32)(pos >> log_n), i = (u32)(pos & (((size_t)1 << log_n) - 1));
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(128, 8) rows_leaf_hash_kernel(const u64* __res
 // Which quarters of a level this launch covers (in-segment sharding, shard.cuh: a rank builds only the subtrees over the
 // leaf quarters it owns).  Thread i works on node q[i >> log_qsize] * qsize + (i & (qsize - 1)); the identity map
 // {4, {0,1,2,3}} is the whole level.
-struct QuarterMap { int nq; int q[4]; int log_qsize; };
+struct QuarterMap { int nq; int q[4]; int log_qsize; };      // "quarter" = one of the 4 * parts() leaf segments (shard.cuh)
 __device__ __forceinline__ size_t quarter_node(const QuarterMap& m, size_t i) {
     return ((size_t)m.q[i >> m.log_qsize] << m.log_qsize) | (i & (((size_t)1 << m.log_qsize) - 1));
 }
@@ -159,18 +160,21 @@ void merkle_alloc(MerkleTreeDev& t, int log_leaves, int cap_height, cudaStream_t
 void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     const Shard& sh = shard();
     const bool sharded = t.sharded && sh.active();
-    ZKM_CHECK(!sharded || t.cap_height >= 2, "sharded trees need cap_height >= 2 (whole cap subtrees per leaf quarter)");
     QuarterMap qm = {4, {0, 1, 2, 3}, 0};
+    int log_segs = 2;
     if (sharded) {
-        qm.nq = sh.coset_count();
-        for (int k = 0; k < qm.nq; k++) qm.q[k] = bitrev2(sh.coset_begin() + k);      // coset j = leaf quarter bitrev2(j)
+        log_segs = sh.log_segs();
+        ZKM_CHECK(t.cap_height >= log_segs, "sharded trees need whole cap subtrees per leaf segment");
+        qm.nq = sh.num_owned_segs();
+        for (int k = 0; k < qm.nq; k++) qm.q[k] = shard_seg_of(sh.coset_begin() + k, sh.part(), sh.world);
     }
+    const int total_segs = 1 << log_segs;
     {
-    const double parents = (double)(t.num_leaves() - ((size_t)1 << t.cap_height)) * qm.nq / 4;
+    const double parents = (double)(t.num_leaves() - ((size_t)1 << t.cap_height)) * qm.nq / total_segs;
     ProfScope ps("merkle_levels", s, 96.0 * parents, parents);      // 64 B in + 32 B out, one permutation per parent
     for (int l = 1; l < t.num_levels(); l++) {
         const int log_np = t.log_leaves - l;
-        qm.log_qsize = log_np - 2;
+        qm.log_qsize = log_np - log_segs;
         size_t np = ((size_t)1 << qm.log_qsize) * qm.nq;             // parents this rank computes on this level
         if (np <= ((size_t)1 << 14)) {
             merkle_level_coop_kernel<<<(unsigned)((np + 7) / 8), 128, 0, s>>>(t.digests.p + t.level_off[l - 1], t.digests.p + t.level_off[l], np, qm);
@@ -190,7 +194,7 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     }
     // the only exchange of a sharded commitment: every rank contributes the cap entries of its leaf quarters (ncclAllGather,
     // 512 B per tree in total); afterwards all ranks hold the same cap and run the same transcript
-    const size_t qwords = ncap / 4, mine = qwords * qm.nq;
+    const size_t qwords = ncap / total_segs, mine = qwords * qm.nq;
     DevBuf send(mine, s), recv(mine * sh.world, s);
     for (int k = 0; k < qm.nq; k++)
         ZKM_CUDA(cudaMemcpyAsync(send.p + k * qwords, t.digests.p + t.level_off.back() + (size_t)qm.q[k] * qwords, qwords * sizeof(u64),
@@ -200,19 +204,21 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     recv.download(all.data(), all.size());
     for (int r = 0; r < sh.world; r++)
         for (int k = 0; k < qm.nq; k++) {
-            const int q = bitrev2(r * qm.nq + k);
+            Shard other; other.rank = r; other.world = sh.world;
+            const int q = shard_seg_of(other.coset_begin() + k, other.part(), sh.world);
             memcpy(t.cap.data() + (size_t)q * qwords, all.data() + ((size_t)r * qm.nq + k) * qwords, qwords * sizeof(u64));
         }
 }
 
 void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s,
-                   int coset_begin, int coset_count) {
+                   int coset_begin, int coset_count, int row_log_stride, int row_offset) {
     if (coset_count < 0) coset_count = (1 << rate_bits) - coset_begin;
     const size_t pos_begin = (size_t)coset_begin << log_n, pos_end = (size_t)(coset_begin + coset_count) << log_n;
-    size_t N = pos_end - pos_begin;                          // leaves hashed by this call
+    size_t N = (pos_end - pos_begin) >> row_log_stride;      // leaves hashed by this call
     unsigned blocks = (unsigned)((N + 127) / 128);
     ProfScope ps("leaf_hash", s, (double)N * (8.0 * ncols + 32.0), ncols > 4 ? (double)N * ((ncols + 7) / 8) : 0.0);
-    lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests, pos_begin, pos_end);
+    lde_leaf_hash_kernel<<<blocks, 128, 0, s>>>(lde, col_stride, ncols, log_n, rate_bits, leaf_digests, pos_begin, pos_end, row_log_stride,
+                                                row_offset);
     ZKM_LAUNCHED();
 }
 

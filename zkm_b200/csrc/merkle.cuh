@@ -26,9 +26,10 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s);
 
 // Leaf digests of a coset-major LDE (ntt.cuh lde_coset): leaf index = bitrev(natural LDE index).
 // ncols <= 4: the row itself, zero padded (plonky2 hash_or_noop); else overwrite-mode sponge.
-// [coset_begin, coset_begin + coset_count): hash only the leaves of those cosets (coset_count < 0: all remaining).
+// [coset_begin, coset_begin + coset_count): hash only the leaves of those cosets (coset_count < 0: all remaining), and of
+// those only the rows i = row_offset mod 2^row_log_stride (a contiguous 2^-row_log_stride of each coset's leaf quarter).
 void lde_leaf_hash(const u64* lde, size_t col_stride, int ncols, int log_n, int rate_bits, u64* leaf_digests, cudaStream_t s,
-                   int coset_begin = 0, int coset_count = -1);
+                   int coset_begin = 0, int coset_count = -1, int row_log_stride = 0, int row_offset = 0);
 
 // Leaf digests for rows stored row-major and already in leaf order: rows[leaf*width .. +width).
 void rows_leaf_hash(const u64* rows, int width, size_t num_leaves, u64* leaf_digests, cudaStream_t s);

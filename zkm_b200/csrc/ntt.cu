@@ -137,16 +137,50 @@ __device__ __forceinline__ int freq_position(int k) {
     return pos;
 }
 
+// ---- bulk-copy (TMA engine) staging of the per-pass twiddle table: one elected thread issues a single cp.async.bulk of the R
+// table entries into shared memory, completion is tracked by an mbarrier (expect_tx / complete_tx), and every thread waits on
+// the barrier's phase only after it has issued its own tile loads -- the table arrives while the tile is in flight instead of
+// costing each thread R / blockDim LDG + STS pairs up front.  (The tile itself cannot take this path: its coset scale is applied
+// in registers on the way in and its rows are padded)  SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
+    u32 done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(phase)
+                     : "memory");
+    } while (!done);
+}
+
 template <int LOG_R>
 __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams p) {
     constexpr int R = 1 << LOG_R;
-    extern __shared__ u64 smem[];
+    extern __shared__ __align__(16) u64 smem[];
+    __shared__ __align__(8) u64 tw_bar;
     const int T = p.T, TS = T + 1, log_T = p.log_T;
     u64* tw = smem;                    // R entries: w_R^e
     u64* x = smem + R;
     const int tid = threadIdx.x, nth = blockDim.x;
     const size_t b = blockIdx.x, c = blockIdx.y, z = blockIdx.z;
-    for (int i = tid; i < R; i += nth) tw[i] = p.tw[i];
+    constexpr bool BULK_TW = LOG_R >= 1;          // cp.async.bulk moves multiples of 16 bytes
+    if (BULK_TW) {
+        if (tid == 0) mbar_init(&tw_bar, 1);
+        __syncthreads();
+        if (tid == 0) bulk_load_g2s(tw, p.tw, (u32)(R * sizeof(u64)), &tw_bar);
+    } else {
+        if (tid == 0) tw[0] = p.tw[0];
+    }
     const u64* in = p.in + c * p.in_c + b * p.in_b + z * p.in_z;
     u64* out = p.out + c * p.out_c + b * p.out_b + z * p.out_z;
     const int total = R << log_T;
@@ -167,6 +201,7 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams
         }
         x[r * TS + t] = v;
     }
+    if (BULK_TW) mbar_wait(&tw_bar, 0);           // the twiddle table has landed (phase 0 of its barrier completed)
     __syncthreads();
     // ---- mixed-radix (16) DIF over r, butterflies in registers ----
     radix_steps<LOG_R>(x, tw, p, log_T, tid, nth);

@@ -327,7 +327,8 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
             all.download(h.data(), h.size());
             for (int q = 0; q < nq; q++) {
                 const int quarter = (int)(qidx[q] >> (b.lde_bits() - 2));
-                const u64* src = h.data() + (size_t)Shard::coset_owner(bitrev2(quarter), sh.world) * per;
+                const int part = (int)(qidx[q] >> (b.lde_bits() - 2 - sh.log_parts())) & (sh.parts() - 1);
+                const u64* src = h.data() + (size_t)Shard::rank_of(bitrev2(quarter), part, sh.world) * per;
                 memcpy(o_rows[o].data() + (size_t)q * b.ncols, src + (size_t)q * b.ncols, (size_t)b.ncols * sizeof(u64));
                 memcpy(o_paths[o].data() + (size_t)q * plen * 4, src + nrow + (size_t)q * plen * 4, (size_t)plen * 4 * sizeof(u64));
             }

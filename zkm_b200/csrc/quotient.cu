@@ -78,6 +78,7 @@ struct QParams {
     // in-segment sharding: the launch covers one half of the quotient domain (coset 0 or coset 2 of the LDE) and writes it
     // half-major, q[(half * na + a) * n + idx], for the exchange; otherwise both halves, natural order q[a * 2n + 2 idx + half]
     int half_base, half_major;
+    size_t idx_base;              // sharded over 8 ranks: the two owners of a coset evaluate one half of its points each
 };
 
 // Column::eval (no next-row terms), used by the logUp Z check (lookup.rs:182-187).
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(COOP ? 512 : ZKM_Q_THREADS, COOP ? 1 : ZKM_Q_M
     __shared__ u64 coop_stage[COOP ? COOP_CHUNK * COOP_PX : 1];
     const size_t n = (size_t)1 << q.log_n;
     // the grid covers the 2n points (or, sharded, the n points of one half) exactly: no early exit (checkpoints)
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + ((size_t)q.half_base << q.log_n);
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x + ((size_t)q.half_base << q.log_n) + q.idx_base;
     const size_t half = t >> q.log_n, idx = t & (n - 1);
     const size_t i = 2 * idx + half;                        // index in the quotient domain 7*H_{2n}
     const size_t pos = (2 * half) * n + idx, pos_next = (2 * half) * n + ((idx + 1) & (n - 1));
@@ -309,15 +310,19 @@ void compute_quotient_values(int kind, const DProgram& prog, const tables::Table
         ZKM_CHECK(aux.sharded && !coop && sh.active(), "quotient: inconsistent sharding");
         DevBuf halves((size_t)2 * num_alphas * n, s);
         q.q = halves.p; q.half_major = 1;
+        const size_t per = n / sh.parts();                 // points of one half evaluated by one rank
         for (int h = 0; h < 2; h++) {
             if (!sh.owns_coset(2 * h)) continue;
             q.half_base = h;
-            ProfScope ps("quotient", s, 8.0 * (double)n * (L.ncols + L.num_aux()) + 8.0 * (double)n * num_alphas);
-            k<<<(unsigned)(n / ZKM_Q_THREADS), ZKM_Q_THREADS, 0, s>>>(q);
+            q.idx_base = (size_t)sh.part() * per;
+            ProfScope ps("quotient", s, 8.0 * (double)per * (L.ncols + L.num_aux()) + 8.0 * (double)per * num_alphas);
+            k<<<(unsigned)(per / ZKM_Q_THREADS), ZKM_Q_THREADS, 0, s>>>(q);
             ZKM_LAUNCHED();
         }
         for (int h = 0; h < 2; h++)
-            shard_broadcast(halves.p + (size_t)h * num_alphas * n, (size_t)num_alphas * n, Shard::coset_owner(2 * h, sh.world), s);
+            for (int p = 0; p < sh.parts(); p++)
+                for (int a = 0; a < num_alphas; a++)
+                    shard_broadcast(halves.p + ((size_t)h * num_alphas + a) * n + (size_t)p * per, per, Shard::rank_of(2 * h, p, sh.world), s);
         quotient_interleave_kernel<<<(unsigned)((2 * n * num_alphas + 255) / 256), 256, 0, s>>>(halves.p, d_q, log_n, num_alphas);
         ZKM_LAUNCHED();
         return;

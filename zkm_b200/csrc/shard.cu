@@ -60,7 +60,7 @@ void shard_unique_id(unsigned char out[128]) {
 }
 
 void shard_init(int rank, int world, const unsigned char id[128]) {
-    ZKM_CHECK(world == 1 || world == 2 || world == 4, "in-segment sharding supports 1, 2 or 4 ranks (the 4 cosets of the rate-4 LDE)");
+    ZKM_CHECK(world == 1 || world == 2 || world == 4 || world == 8, "in-segment sharding supports 1, 2, 4 or 8 ranks (the 4 cosets of the rate-4 LDE, halved once)");
     ZKM_CHECK(rank >= 0 && rank < world, "shard rank out of range");
     shard_shutdown();
     if (world == 1) return;

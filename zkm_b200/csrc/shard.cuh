@@ -1,4 +1,4 @@
-// In-segment sharding: one STARK proof computed by G = 2 or 4 GPUs (one process per GPU), SURVEY section 8(e).
+// In-segment sharding: one STARK proof computed by G = 2, 4 or 8 GPUs (one process per GPU), SURVEY section 8(e).
 //
 // The 4n-point LDE domain 7*H_{4n} is the disjoint union of the four cosets 7 w_{4n}^j H_n, and this library already stores
 // every LDE coset-major (ntt.cuh).  Coset j is exactly the quarter bitrev2(j) of the bit-reversed leaf order, i.e. four whole
@@ -21,13 +21,23 @@ namespace zkm {
 struct Shard {
     int rank = 0, world = 1;
     bool active() const { return world > 1; }
-    // cosets (of the 4 = 2^rate_bits) this rank owns
+    // cosets (of the 4 = 2^rate_bits) this rank computes.  Up to 4 ranks: 4/world whole cosets each.  8 ranks: two ranks share
+    // a coset -- both run its transform (the NTT is 20 % of a commitment, the hashing 80 %), each hashes one half of its
+    // leaves (the rows i = part mod 2 of the coset, i.e. a contiguous eighth of the bit-reversed leaf order = 2 cap subtrees).
+    int parts() const { return world > 4 ? world / 4 : 1; }           // ranks per coset
+    int log_parts() const { return world > 4 ? 1 : 0; }
+    int part() const { return rank % parts(); }
     int coset_begin() const { return rank * 4 / world; }
-    int coset_count() const { return 4 / world; }
+    int coset_count() const { return world >= 4 ? 1 : 4 / world; }
     bool owns_coset(int j) const { return j >= coset_begin() && j < coset_begin() + coset_count(); }
-    static int coset_owner(int j, int world) { return j * world / 4; }
+    // leaf segments: the leaves split into 4 * parts() contiguous segments; coset j, part p is segment bitrev2(j) * parts() + p
+    int log_segs() const { return 2 + log_parts(); }
+    int num_owned_segs() const { return coset_count(); }
+    static int rank_of(int coset, int part, int world) { return world > 4 ? coset * (world / 4) + part : coset * world / 4; }
+    static int coset_owner(int j, int world) { return rank_of(j, 0, world); }
 };
 inline int bitrev2(int j) { return ((j & 1) << 1) | (j >> 1); }
+inline int shard_seg_of(int coset, int part, int world) { return world > 4 ? bitrev2(coset) * (world / 4) + part : bitrev2(coset); }
 
 const Shard& shard();
 // 128-byte NCCL unique id (rank 0 creates it, the caller distributes it to the other ranks out of band).

@@ -72,7 +72,7 @@ def prove_segments(prove: Callable[[int], np.ndarray], num_segments: int, rank: 
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# In-segment sharding (include/zkm_b200.h "In-segment sharding"): G = 2 or 4 ranks prove ONE segment together.
+# In-segment sharding (include/zkm_b200.h "In-segment sharding"): G = 2, 4 or 8 ranks prove ONE segment together.
 # The ownership rules below are the host-side mirror of zkm_b200/csrc/shard.cuh, used to form the groups and -- in the CPU
 # tests (gloo, the oracle as each rank's local prover) -- to check that the exchanged pieces reassemble the single-rank result.
 
@@ -84,30 +84,55 @@ def bitrev(x: int, bits: int) -> int:
     return r
 
 
+def _check_group(group: int):
+    if group not in (1, 2, 4, 8):
+        raise ValueError("in-segment sharding supports groups of 1, 2, 4 or 8 ranks")
+
+
+def parts(group: int) -> int:
+    """Ranks that share one coset: 1 up to 4 ranks; with 8 ranks two ranks run the same coset transform and hash half of its
+    leaves each."""
+    return group // 4 if group > 4 else 1
+
+
 def owned_cosets(rank: int, group: int) -> List[int]:
-    """LDE cosets j (natural LDE index m = 4 i + j) owned by `rank` of a `group`-rank shard group: 4/group consecutive ones."""
-    if group not in (1, 2, 4):
-        raise ValueError("in-segment sharding supports groups of 1, 2 or 4 ranks")
+    """LDE cosets j (natural LDE index m = 4 i + j) `rank` of a `group`-rank shard group computes."""
+    _check_group(group)
+    if group >= 4:
+        return [rank * 4 // group]
     per = 4 // group
     return list(range(rank * per, (rank + 1) * per))
 
 
+def rank_of(coset: int, part: int, group: int) -> int:
+    return coset * (group // 4) + part if group > 4 else coset * group // 4
+
+
 def coset_owner(j: int, group: int) -> int:
-    return j * group // 4
+    return rank_of(j, 0, group)
 
 
 def leaf_owner(leaf: int, log_leaves: int, group: int) -> int:
-    """Rank holding leaf `leaf` (bit-reversed LDE order) and its path: the top two leaf bits are the bit-reversed coset id."""
-    return coset_owner(bitrev(leaf >> (log_leaves - 2), 2), group)
+    """Rank holding leaf `leaf` (bit-reversed LDE order) and its path: the top two leaf bits are the bit-reversed coset id,
+    the next bit (8 ranks) the half of that coset's leaves."""
+    _check_group(group)
+    p = parts(group)
+    part = (leaf >> (log_leaves - 2 - (p.bit_length() - 1))) & (p - 1)
+    return rank_of(bitrev(leaf >> (log_leaves - 2), 2), part, group)
+
+
+def owned_segments(rank: int, group: int) -> List[int]:
+    """Leaf segments (of the 4 * parts contiguous ones) a rank hashes and builds subtrees over."""
+    p = parts(group)
+    return [bitrev(j, 2) * p + rank % p for j in owned_cosets(rank, group)]
 
 
 def owned_cap_entries(rank: int, group: int, cap_height: int = 4) -> List[int]:
-    """Cap entries (subtree roots over contiguous leaf blocks) a rank computes: those of its cosets' leaf quarters."""
-    per_quarter = (1 << cap_height) // 4
+    """Cap entries (subtree roots over contiguous leaf blocks) a rank computes: those of its leaf segments."""
+    per_seg = (1 << cap_height) // (4 * parts(group))
     out = []
-    for j in owned_cosets(rank, group):
-        q = bitrev(j, 2)
-        out.extend(range(q * per_quarter, (q + 1) * per_quarter))
+    for sg in owned_segments(rank, group):
+        out.extend(range(sg * per_seg, (sg + 1) * per_seg))
     return out
 
 
@@ -122,7 +147,7 @@ def assemble_cap(pieces: Sequence[np.ndarray], group: int, cap_height: int = 4) 
 
 
 def shard_group_init(lib, group: int = 0):
-    """Forms in-segment shard groups of `group` consecutive ranks (default: min(world, 4)) out of the torch.distributed world
+    """Forms in-segment shard groups of `group` consecutive ranks (default: the whole world, up to 8) out of the torch.distributed world
     and binds this process's library context to its group: rank 0 of each group creates the NCCL unique id
     (zkm_b200_shard_unique_id) and it reaches the other members through a torch.distributed broadcast.  Returns
     (group_index, rank_in_group, group_size).  Collective over the whole world."""
@@ -131,8 +156,8 @@ def shard_group_init(lib, group: int = 0):
     import torch.distributed as dist
     from . import lib as zl
     world, rank = dist.get_world_size(), dist.get_rank()
-    g = group or min(world, 4)
-    if world % g or g not in (1, 2, 4):
+    g = group or min(world, 8)
+    if world % g or g not in (1, 2, 4, 8):
         raise ValueError(f"cannot split {world} ranks into shard groups of {g}")
     gi, ri = rank // g, rank % g
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"

@@ -607,7 +607,7 @@ def main():
                  "peak_kind": peak_kind, "traffic": seg.ncu_traffic(name), "launches": v["launches"],
                  "avg_launch_ms": v["ms"] / max(1, v["launches"]), "share_of_step": v["ms"] / total_ms,
                  "algorithmic_bytes_per_launch": v["bytes"] / max(1, v["launches"]), "note": note}
-            if v.get("traffic_bytes"):
+            if name == "ntt_pass" and v.get("traffic_bytes"):      # the second counter is pass traffic for the NTT family only
                 r["pass_traffic_GBps"] = v["traffic_bytes"] / (v["ms"] * 1e-3) / 1e9
                 r["pass_traffic_frac"] = r["pass_traffic_GBps"] / peak
             return r

@@ -411,3 +411,45 @@ def test_keccak_table_generated_on_the_device(zkm, orc):
         assert got.shape == want.shape == (2431, n)
         assert (got == want).all()
     assert orc.orc_check_table_constraints(4, binding.col_ptrs(got), 2431, 9) == 0
+
+
+def test_row_major_table_with_2_21_rows(zkm):
+    """the row -> column transpose put the row tiles on gridDim.y (<= 65535), so any row-major table with >= 2^21 rows
+    failed to launch.  A Logic table of 2^21 rows handed over as rows must give the proof of the same table handed over as
+    columns (synthetic traces: the two proofs are compared with each other)."""
+    heights = [16, 6, 6, 6, 6, 6, 6, 6, 6, 6, 21, 6]
+    traces = zl.synth_traces(zkm, tr.SYSTEM_ALL_STARK, heights)
+    ref = zl.prove_with_traces(zkm, traces)
+    mixed = [np.ascontiguousarray(t.T) if k == 10 else t for k, t in enumerate(traces)]
+    got = zl.prove_with_trace_rows(zkm, mixed, {10})
+    assert _first_diff(ref, got) is None
+
+
+def test_mixed_shape_workers_soak(zkm):
+    """every worker context caches freed device blocks in its own arena.  Three workers proving segments of DIFFERENT
+    shapes, shapes rotating between iterations (so that blocks cached for one shape are useless for the next), must keep
+    producing the proofs computed alone -- the arenas are registered, a failed cudaMalloc trims all of them, and the bytes
+    cached device-wide are capped."""
+    import threading
+    shapes = [[16, 14, 6, 6, 6, 6, 6, 6, 6, 6, 12, 14], [16, 15, 6, 6, 6, 6, 6, 7, 6, 6, 13, 13], [17, 13, 6, 6, 7, 6, 6, 6, 6, 6, 15, 16]]
+    segs = [zl.synth_traces(zkm, tr.SYSTEM_ALL_STARK, h, seed=0x5EED000000000000 + (i << 40)) for i, h in enumerate(shapes)]
+    alone = [zl.prove_with_traces(zkm, s) for s in segs]
+    workers = [zl.Worker(zkm) for _ in range(3)]
+    errors = []
+
+    def body(i):
+        try:
+            with workers[i]:
+                for it in range(4):
+                    k = (i + it) % 3
+                    assert _first_diff(zl.prove_with_traces(zkm, segs[k]), alone[k]) is None
+        except BaseException as e:
+            errors.append(e)
+    threads = [threading.Thread(target=body, args=(i,)) for i in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    for w in workers:
+        w.close()
+    assert not errors, errors

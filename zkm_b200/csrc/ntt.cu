@@ -241,7 +241,9 @@ static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s, d
     // alg_bytes: this launch's share of the transform's algorithmic bytes (inputs read once, outputs
     // written once -- charged to the first pass); the second counter is the traffic of the pass itself, 16 B per element
     ProfScope ps("ntt_pass", s, alg_bytes, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
-    if (smem > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the kernel also holds a few bytes of static shared memory (the twiddle table's mbarrier): opt in to large dynamic shared
+    // memory as soon as static + dynamic could pass the 48 KB default (R = 1024, T = 4 asks for exactly 48 KB of dynamic)
+    if (smem + 256 > 48 * 1024) ZKM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one radix-16 work item per thread per step when the tile is large enough (8 warps per SM sub-partition)
     size_t items = (R >> (log_r >= 4 ? 4 : log_r)) * (size_t)p.T;
     int threads = items >= 1024 ? 1024 : (items >= 512 ? 512 : 256);

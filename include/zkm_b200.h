@@ -176,7 +176,21 @@ int zkm_b200_prove_with_memory_ops(const zkm_table_t tables[12], const zkm_table
  *                                                                                                   (poseidon_stark.rs:51-145)
  *   Keccak   (table 4)  26 words: the 25 input lanes (input[y * 5 + x] = lane (x, y)), timestamp -> KeccakStark::generate_trace
  *                                                                                                   (keccak_stark.rs:62-237, 24 rows per permutation)
- * Heights follow the reference: next power of two of max(number of operations, min_rows), min_rows = max(2^cap_height, 64).
+ *   ShaExtend (table 6)  5 words: w[i-15], w[i-2], w[i-16], w[i-7] (u32), timestamp                -> ShaExtendStark::generate_trace
+ *                                                                                                   (sha_extend_stark.rs:122-237, one row per entry)
+ *   ShaExtendSponge (7) 13 words: round i (0..47), the same four words, input_virt[4], output_virt, context, segment, timestamp
+ *                                                                                                -> sha_extend_sponge_stark.rs:128-227
+ *   ShaCompress (8)     15 words: a..h (u32), w_i, k_i, round (0..64), w_i_virt, segment, context, timestamp -- one entry per
+ *                                 ROW, the reference's ([u8; 41], MemoryAddress, usize)           -> sha_compress_stark.rs:234-391
+ *   ShaCompressSponge (9) 86 words: hx[8], w[64] (u32), hx_virt[8], w_start virt / segment / context, context, segment,
+ *                                 timestamp                                                       -> sha_compress_sponge_stark.rs:120-237
+ *   PoseidonSponge (3), KeccakSponge (5): a VARIABLE-width log.  Word 0 = the number of words of the whole log; then per operation
+ *                                 context, segment, timestamp, len (bytes), n_addr, virt[n_addr], the input bytes packed little endian
+ *                                 8 per word ({Keccak,Poseidon}SpongeOp {base_address, timestamp, input}: context / segment of
+ *                                 base_address[0], virt[k] = base_address[k].virt); len / rate + 1 rows per operation
+ *                                 (keccak_sponge_stark.rs:222-447 rate 136, poseidon_sponge_stark.rs:187-365 rate 32); n_ops = operations
+ * The Cpu table (1) has no log: its rows ARE the interpreter's output (pass them row-major, zkm_b200_prove_with_trace_rows).
+ * Heights follow the reference: next power of two of max(number of rows, min_rows), min_rows = max(2^cap_height, 64).
  * zkm_b200_table_from_ops returns the finished columns (column-major, malloc'ed; zkm_b200_free); zkm_b200_prove_with_ops is
  * prove_with_trace_rows where every table t with op_logs[t].ops != NULL is generated on the device instead of being read from
  * tables[t] / row_tables[t] -- only the log crosses PCIe (Logic: 24 B instead of 552 B per row, Arithmetic: 24 B instead of 432 B). */
@@ -217,6 +231,28 @@ int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const
  * file recursion/src/lib.rs:142-146 writes).  Host-only: no device, no zkm_b200_init.  Strings are malloc'ed (zkm_b200_free_string). */
 int zkm_b200_proof_table_json(const uint64_t* proof, size_t proof_words, uint32_t table, char** json_out, size_t* json_len, char** err);
 int zkm_b200_public_values_json(const uint64_t* proof, size_t proof_words, char** json_out, size_t* json_len, char** err);
+
+/* ---- emulator segment splitter: page hashes and image id ---------------------------------------
+ *
+ * At every segment boundary the reference's InstrumentedState::split_segment (emulator/src/state.rs:1460-1530) calls
+ * Memory::update_page_hash (emulator/src/memory.rs:415-436) -- hash_page (:81-89, 129 Poseidon permutations) of every 4 KiB
+ * page the segment wrote, the digests stored into the L1 hash pages, those re-hashed into L2 and the root page -- and
+ * Memory::compute_image_id (:438-471).  The pages are independent: these entry points do the hashing on the device.
+ *
+ * zkm_b200_hash_pages: hash_page of n_pages contiguous pages -> n_pages x 32 bytes (the four digest words, little endian).
+ * A zkm_pagetree_t holds the hash pages at and above MAX_MEMORY = 0x80000000 (absent pages have the reference's
+ * CONST_HASH_PAGES content, :91-125).  zkm_b200_pagetree_split(tree, indices, pages, n, registers, pc) is update_page_hash
+ * over the dirty main-memory pages `pages[k]` (page index indices[k] = address >> 12, < 0x80000; the reference's wtrace[0])
+ * followed by compute_image_id(pc, registers = State::get_registers_bytes(), 39 x 4 bytes): image_id_out and
+ * page_hash_root_out receive 32 bytes each.  "compute image ID fail" is returned when no page was ever hashed (the
+ * reference's panic).  zkm_b200_pagetree_page reads one hash page back (they are part of the segment's memory image). */
+typedef struct zkm_pagetree zkm_pagetree_t;
+int zkm_b200_hash_pages(const uint8_t* pages, size_t n_pages, uint8_t* digests_out, char** err);
+int zkm_b200_pagetree_create(zkm_pagetree_t** out, char** err);
+void zkm_b200_pagetree_destroy(zkm_pagetree_t* t);
+int zkm_b200_pagetree_split(zkm_pagetree_t* t, const uint32_t* page_indices, const uint8_t* pages, size_t n_pages,
+                            const uint8_t* registers, uint32_t pc, uint8_t* image_id_out, uint8_t* page_hash_root_out, char** err);
+int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t* out, int* present, char** err);
 
 /* ---- column-layout handshake ---------------------------------------------------------------------------------------
  *

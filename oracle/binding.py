@@ -59,6 +59,15 @@ def load():
     lib.orc_num_ctls.argtypes = [C.c_int]
     lib.orc_lookup_fingerprint.argtypes = [C.c_int, C.c_int, u64, u64p]
     lib.orc_gen_poseidon_rows.argtypes = [u64p, u64p, C.c_size_t, u64p]
+    lib.orc_hash_pages.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.orc_poseidon_bytes.argtypes = [C.c_char_p, C.c_size_t, u64p]
+    lib.orc_const_hash_page.argtypes = [C.c_int, C.c_void_p]
+    lib.orc_pagetree_create.restype = C.c_void_p
+    lib.orc_pagetree_destroy.argtypes = [C.c_void_p]
+    lib.orc_pagetree_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.orc_pagetree_page.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.orc_pagetree_count.argtypes = [C.c_void_p]
+    lib.orc_pagetree_count.restype = C.c_size_t
     _lib = lib
     return lib
 
@@ -110,3 +119,31 @@ def col_ptrs(cols: np.ndarray):
     for i in range(ncols):
         arr[i] = C.cast(cols.ctypes.data + i * n * 8, C.POINTER(C.c_uint64))
     return arr
+
+
+class OrcPageTree:
+    """oracle/pagehash.h PageTree (emulator update_page_hash + compute_image_id restated on the CPU)."""
+
+    def __init__(self, lib):
+        self.lib, self.h = lib, lib.orc_pagetree_create()
+
+    def split(self, indices, pages, registers: bytes, pc: int):
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        pg = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1, 4096)
+        image_id, root = np.zeros(32, dtype=np.uint8), np.zeros(32, dtype=np.uint8)
+        rc = self.lib.orc_pagetree_split(self.h, idx.ctypes.data, pg.ctypes.data, idx.size, registers, pc, image_id.ctypes.data, root.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("compute image ID fail")
+        return bytes(image_id), bytes(root)
+
+    def page(self, index: int):
+        out = np.zeros(4096, dtype=np.uint8)
+        return out if self.lib.orc_pagetree_page(self.h, index, out.ctypes.data) else None
+
+    def count(self):
+        return self.lib.orc_pagetree_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.orc_pagetree_destroy(self.h)
+            self.h = None

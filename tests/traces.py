@@ -258,7 +258,7 @@ def cpu_system_traces():
             cg.memory_generate_trace(cpu.mem_ops)]
 
 
-def all_stark_valid_traces(orc, sha_blocks=0, return_cpu=False):
+def all_stark_valid_traces(orc, sha_blocks=0, return_cpu=False, return_ops=False):
     """A valid trace of all 12 AllStark tables: the test program with its syscalls and the Keccak / SHA-256 precompiles
     (tests/cpu_program.py, with_syscalls), the image-id Poseidon hash of the bootstrap, and every table generated from
     the operations the interpreter logged -- what Traces::into_tables does upstream (witness/traces.rs:230-318)."""
@@ -336,4 +336,26 @@ def all_stark_valid_traces(orc, sha_blocks=0, return_cpu=False):
             hg.rows_to_trace(scs_rows, hg.SHA_COMPRESS_SPONGE_COLUMNS, lg(len(scs_rows))),
             logic_trace_from_ops(logic, lg(len(logic))),
             cg.memory_generate_trace(cpu.mem_ops)]
+    if return_ops:
+        # the operation logs zkm_b200_prove_with_ops takes for every table but Cpu (include/zkm_b200.h): the same operations the
+        # tables above were generated from
+        ses_ops = [[rnd, *ins, *virts, out_virt, 0, 0, ts] for ins, virts, out_virt, ts, rnd, _w in cpu.sha_extend_ops]
+        sc_ops, scs_ops = [], []
+        for hx, w, h_ptr, w_ptr, ts in cpu.sha_compress_ops:
+            st = list(hx)
+            for i in range(65):
+                w_i, k_i = (w[i], hg.SHA_K[i]) if i < 64 else (0, 0)
+                sc_ops.append([*st, w_i, k_i, i, w_ptr + 4 * i, 0, 0, ts])
+                st = hg.sha_compress_row(st, w_i, k_i, i, 0, 0)[1]
+            scs_ops.append([*hx, *w, *[h_ptr + 4 * j for j in range(8)], w_ptr, 0, 0, 0, 0, ts])
+        arr = lambda rows, k: np.array(rows, dtype=np.uint64).reshape(len(rows), k)
+        ops = {0: arr(cpu.arith_ops, 3),
+               2: np.concatenate([p_in[:len(ps_perms)], p_ts[:len(ps_perms), None]], axis=1),
+               3: [(addrs, ts, data, ctx, seg) for addrs, ts, data, ctx, seg, _row in cpu.poseidon_ops],
+               4: arr([list(lanes) + [ts] for lanes, ts in k_in], 26),
+               5: list(cpu.keccak_ops),
+               6: arr([[*ins, ts] for ins, _v, _o, ts, _r, _w in cpu.sha_extend_ops], 5),
+               7: arr(ses_ops, 13), 8: arr(sc_ops, 15), 9: arr(scs_ops, 86),
+               10: arr(logic, 3), 11: arr(cpu.mem_ops, 7)}
+        return out, ops
     return (out, cpu) if return_cpu else out

@@ -209,8 +209,14 @@ static size_t table_from_ops_dev(int table, const u64* ops, size_t n_ops, size_t
         case tables::T_LOGIC: return logic_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         case tables::T_POSEIDON: return poseidon_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         case tables::T_KECCAK: return keccak_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_POSEIDON_SPONGE: return poseidon_sponge_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_KECCAK_SPONGE: return keccak_sponge_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_SHA_EXTEND: return sha_extend_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_SHA_EXTEND_SPONGE: return sha_extend_sponge_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_SHA_COMPRESS: return sha_compress_generate_trace_dev(ops, n_ops, min_rows, cols, s);
+        case tables::T_SHA_COMPRESS_SPONGE: return sha_compress_sponge_generate_trace_dev(ops, n_ops, min_rows, cols, s);
         default: throw std::runtime_error(std::string("no device-side generator for table ") + tables::table_name(table) +
-                                          " (available: Arithmetic, Poseidon, Keccak, Logic, Memory)");
+                                          " (the Cpu table is the interpreter's own rows: pass them row-major)");
     }
 }
 

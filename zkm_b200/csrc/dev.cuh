@@ -115,6 +115,13 @@ size_t arithmetic_generate_trace_dev(const u64* h_ops, size_t n_ops, struct DevB
 size_t logic_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 size_t keccak_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 size_t poseidon_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+// The six hash-precompile tables (tracegen_hash.cu); the two byte sponges take a variable-width log (word 0 = its word count).
+size_t sha_extend_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t sha_extend_sponge_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t sha_compress_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t sha_compress_sponge_generate_trace_dev(const u64* h_ops, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t keccak_sponge_generate_trace_dev(const u64* h_log, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
+size_t poseidon_sponge_generate_trace_dev(const u64* h_log, size_t n_ops, size_t min_rows, struct DevBuf& cols, cudaStream_t s);
 
 // Two-level table of powers of one field element g:  g^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 struct PowTable {

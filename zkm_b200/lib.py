@@ -37,6 +37,7 @@ EXPORTS = [
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
+    "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
 ]
 
 
@@ -333,14 +334,29 @@ class OpLog(C.Structure):
 NCOLS_ALL_STARK = [54, 259, 262, 110, 2431, 470, 78, 76, 224, 127, 69, 13]
 
 
-def table_from_ops(lib, table: int, ops, min_rows: int = 64):
-    """zkm_b200_table_from_ops: ops = (n_ops, words_per_op) uint64 -> (ncols, n) table generated on the device."""
+def sponge_log(ops):
+    """The variable-width log of the two byte sponges (tables 3 and 5, include/zkm_b200.h): ops = [(virt of every input word,
+    timestamp, input bytes, context, segment)] -> (1-D uint64 log whose word 0 is its word count, number of operations)."""
+    words = [0]
+    for virts, ts, data, ctx, seg in ops:
+        data = bytes(data)
+        words += [ctx, seg, ts, len(data), len(virts)] + [int(v) for v in virts]
+        padded = data + bytes(-len(data) % 8)
+        words += [int.from_bytes(padded[i:i + 8], "little") for i in range(0, len(padded), 8)]
+    words[0] = len(words)
+    return np.array(words, dtype=np.uint64), len(ops)
+
+
+def table_from_ops(lib, table: int, ops, min_rows: int = 64, n_ops=None):
+    """zkm_b200_table_from_ops: ops = (n_ops, words_per_op) uint64 -> (ncols, n) table generated on the device; for the two
+    byte sponges ops is the 1-D log of sponge_log() and n_ops its number of operations."""
     a = np.ascontiguousarray(ops, dtype=np.uint64)
-    assert a.ndim == 2
+    assert a.ndim == 2 or n_ops is not None
+    n_ops = a.shape[0] if n_ops is None else n_ops
     out, lg, err = C.POINTER(C.c_uint64)(), C.c_uint32(), C.c_void_p()
     lib.zkm_b200_table_from_ops.argtypes = [C.c_uint32, C.POINTER(C.c_uint64), C.c_size_t, C.c_uint32, C.POINTER(C.POINTER(C.c_uint64)),
                                             C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
-    check(lib, lib.zkm_b200_table_from_ops(table, a.ctypes.data_as(C.POINTER(C.c_uint64)), a.shape[0], min_rows, C.byref(out), C.byref(lg),
+    check(lib, lib.zkm_b200_table_from_ops(table, a.ctypes.data_as(C.POINTER(C.c_uint64)), n_ops, min_rows, C.byref(out), C.byref(lg),
                                            C.byref(err)), err)
     n, nc = 1 << lg.value, NCOLS_ALL_STARK[table]
     t = np.ctypeslib.as_array(out, shape=(nc * n,)).copy().reshape(nc, n)
@@ -362,10 +378,13 @@ def prove_with_ops(lib, traces, op_logs, roots_before=None, roots_after=None, us
     arr = (Table * 12)(*cols)
     logs = (OpLog * 12)()
     for t, ops in op_logs.items():
+        n_ops = None
+        if isinstance(ops, tuple):                  # (1-D sponge log, number of operations)
+            ops, n_ops = ops
         a = np.ascontiguousarray(ops, dtype=np.uint64)
         keep.append(a)
         logs[t].ops = a.ctypes.data_as(C.POINTER(C.c_uint64))
-        logs[t].n_ops = a.shape[0]
+        logs[t].n_ops = a.shape[0] if n_ops is None else n_ops
     rb = (C.c_uint32 * 8)(*(roots_before or range(1, 9)))
     ra = (C.c_uint32 * 8)(*(roots_after or range(11, 19)))
     out, words, err = C.POINTER(C.c_uint64)(), C.c_size_t(), C.c_void_p()
@@ -377,3 +396,47 @@ def prove_with_ops(lib, traces, op_logs, roots_before=None, roots_after=None, us
     proof = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
     lib.zkm_b200_free(out)
     return proof
+
+
+def hash_pages(lib, pages):
+    """zkm_b200_hash_pages: pages = (n, 4096) uint8 -> (n, 32) uint8 digests (emulator hash_page on the device)."""
+    a = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1, 4096)
+    out = np.zeros((a.shape[0], 32), dtype=np.uint8)
+    err = C.c_void_p()
+    lib.zkm_b200_hash_pages.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+    check(lib, lib.zkm_b200_hash_pages(a.ctypes.data, a.shape[0], out.ctypes.data, C.byref(err)), err)
+    return out
+
+
+class PageTree:
+    """zkm_pagetree_t: the emulator's hash pages + update_page_hash / compute_image_id with the hashing on the device."""
+
+    def __init__(self, lib):
+        self.lib, self.h = lib, C.c_void_p()
+        err = C.c_void_p()
+        lib.zkm_b200_pagetree_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        lib.zkm_b200_pagetree_destroy.argtypes = [C.c_void_p]
+        lib.zkm_b200_pagetree_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_void_p)]
+        lib.zkm_b200_pagetree_page.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        check(lib, lib.zkm_b200_pagetree_create(C.byref(self.h), C.byref(err)), err)
+
+    def split(self, indices, pages, registers: bytes, pc: int):
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        pg = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1, 4096)
+        assert idx.size == pg.shape[0] and len(registers) == 156
+        image_id, root = np.zeros(32, dtype=np.uint8), np.zeros(32, dtype=np.uint8)
+        err = C.c_void_p()
+        check(self.lib, self.lib.zkm_b200_pagetree_split(self.h, idx.ctypes.data, pg.ctypes.data, idx.size, registers, pc, image_id.ctypes.data,
+                                                         root.ctypes.data, C.byref(err)), err)
+        return bytes(image_id), bytes(root)
+
+    def page(self, index: int):
+        out, present, err = np.zeros(4096, dtype=np.uint8), C.c_int(), C.c_void_p()
+        check(self.lib, self.lib.zkm_b200_pagetree_page(self.h, index, out.ctypes.data, C.byref(present), C.byref(err)), err)
+        return out if present.value else None
+
+    def close(self):
+        if self.h:
+            self.lib.zkm_b200_pagetree_destroy(self.h)
+            self.h = C.c_void_p()

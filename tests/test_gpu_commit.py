@@ -93,6 +93,39 @@ def test_commit_matches_oracle(zkm, orc, ncols, log_n, from_values):
         orc.orc_batch_free(ho)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ncols,log_n", [(3, 5), (135, 12), (20, 14)])
+def test_commit_at_the_recursion_blow_up(zkm, orc, ncols, log_n):
+    """PolynomialBatch::from_values at rate_bits = 3, cap_height = 4: the shape plonky2's PLONK prover commits with under
+    `standard_recursion_config` (135 wire columns; SURVEY §8 f1 -- the recursion prover reuses these kernels at blow-up 8).
+    Cap, coefficients, the whole 8n-point LDE of three columns, opened rows and Merkle paths against the oracle."""
+    n, rb = 1 << log_n, 3
+    cols = random_columns(ncols, n, seed=77 + ncols)
+    cap_g = np.zeros(64, dtype=np.uint64); cap_o = np.zeros(64, dtype=np.uint64)
+    t, keep = zl.make_table(cols)
+    h = C.c_void_p(); err = C.c_void_p()
+    _chk(zkm, zkm.zkm_b200_commit_values(C.byref(t), rb, 4, C.byref(h), u64ptr(cap_g), C.byref(err)), err)
+    ho = orc.orc_commit(col_ptrs(cols), ncols, log_n, rb, 4, 1, u64ptr(cap_o))
+    assert ho
+    try:
+        assert (cap_g == cap_o).all()
+        for c in sorted({0, ncols // 2, ncols - 1}):
+            lg = np.zeros(n << rb, dtype=np.uint64); lo = np.zeros(n << rb, dtype=np.uint64)
+            _chk(zkm, zkm.zkm_b200_batch_get_lde(h, c, u64ptr(lg), C.byref(err)), err)
+            orc.orc_batch_get_lde(ho, c, u64ptr(lo))
+            assert (lg == lo).all()
+        plen = log_n + rb - 4
+        for leaf in (0, 1, (n << rb) - 1, (n << rb) // 3):
+            rg = np.zeros(ncols, dtype=np.uint64); ro = np.zeros(ncols, dtype=np.uint64)
+            sg = np.zeros(max(1, plen * 4), dtype=np.uint64); so = np.zeros(max(1, plen * 4), dtype=np.uint64)
+            _chk(zkm, zkm.zkm_b200_batch_open(h, leaf, u64ptr(rg), u64ptr(sg), C.byref(err)), err)
+            orc.orc_batch_open(ho, leaf, u64ptr(ro), u64ptr(so))
+            assert (rg == ro).all() and (sg == so).all()
+    finally:
+        zkm.zkm_b200_batch_free(h)
+        orc.orc_batch_free(ho)
+
+
 def test_error_reporting(zkm):
     err = C.c_void_p()
     buf = np.zeros(8, dtype=np.uint64)

@@ -50,7 +50,7 @@ struct NttPassParams {
     int ncols_total;              // valid range for the "t = column" single-pass mode
     int t_is_column;              // single-pass mode: t indexes columns; guard against ncols
     int load_t_fast, store_t_fast;
-    PowTable pre[4]; int has_pre; size_t pre_b, pre_r, pre_t;     // input scale  pre[z]^(b*pre_b+r*pre_r+t*pre_t)
+    PowTable pre[8]; int has_pre; size_t pre_b, pre_r, pre_t;     // input scale  pre[z]^(b*pre_b+r*pre_r+t*pre_t)
     PowTable post; int has_post; size_t post_b, post_t;           // output scale post^((b*post_b+t*post_t)*k)
     u64 scale;                    // constant output multiplier (1 = none)
     const u64* tw;                // w_R^k, k < R/2
@@ -399,14 +399,14 @@ void ntt_inverse(NttTables& t, const u64* in, size_t in_cs, u64* out, size_t out
 }
 void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t out_cs, int ncols, int log_n, int rate_bits,
                cudaStream_t s, int shift_exp_bits, int coset_begin, int coset_count) {
-    ZKM_CHECK(rate_bits <= 2, "rate_bits > 2 unsupported");
+    ZKM_CHECK(rate_bits <= 3, "rate_bits > 3 unsupported");        // 3 = plonky2's standard_recursion_config (blow-up 8)
     const int all = 1 << rate_bits;
     if (coset_count < 0) coset_count = all - coset_begin;
     ZKM_CHECK(coset_begin >= 0 && coset_count >= 1 && coset_begin + coset_count <= all, "bad coset range");
     const int nz = coset_count;
     const size_t n = (size_t)1 << log_n;
-    PowTable pre[4];
-    std::shared_ptr<PowTableOwner> keep[4];
+    PowTable pre[8];
+    std::shared_ptr<PowTableOwner> keep[8];
     for (int z = 0; z < nz; z++) { keep[z] = get_shift(t, log_n, rate_bits, coset_begin + z, 0, s, shift_exp_bits); pre[z] = keep[z]->view; }
     // section 8(d): the LDE writes 8*n bytes per coset and column; its input is the coefficient vector the preceding iNTT (or
     // fold) just wrote, which the survey's 48*n*C figure for iNTT + LDE does not count a second time

@@ -79,7 +79,7 @@ extern "C" {
     fn zkm_b200_free_string(s: *mut c_char);
 }
 
-fn take_error(err: *mut c_char) -> anyhow::Error {
+pub(crate) fn take_error(err: *mut c_char) -> anyhow::Error {
     if err.is_null() {
         return anyhow!("zkm_b200: unknown error");
     }
@@ -350,7 +350,7 @@ pub fn decode_all_proof(buf: &[u64]) -> Result<AllProof<F, C, D>> {
 
 // ------------------------------------------------------------------------------------------- the replacement call
 
-fn stark_config_to_c(config: &StarkConfig) -> Result<ZkmStarkConfig> {
+pub(crate) fn stark_config_to_c(config: &StarkConfig) -> Result<ZkmStarkConfig> {
     use plonky2::fri::reduction_strategies::FriReductionStrategy;
     let fc = &config.fri_config; // config.rs:4-29
     let (arity_bits, final_poly_bits) = match &fc.reduction_strategy {

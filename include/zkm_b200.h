@@ -325,6 +325,21 @@ int zkm_b200_batch_get_lde(const zkm_batch_t* b, uint32_t col, uint64_t* out, ch
 int zkm_b200_batch_open(const zkm_batch_t* b, uint32_t leaf_index, uint64_t* leaf_out,
                         uint64_t* siblings_out, char** err);
 
+/* The finer-grained seam of SURVEY section 8(b) for ONE table of a System, under caller-given challenges (no transcript), for
+ * stage-level parity against the oracle:
+ *   aux_out       num_aux x 2^log_n words, column-major: lookup_helper_columns (lookup.rs:46-124) then the CTL helper and Z
+ *                 columns of cross_table_lookup_data (cross_table_lookup.rs:634-703,801-872), in the order prove_single_table
+ *                 commits them (prover.rs:469-522)
+ *   quotient_out  num_challenges x 2^(log_n + 1) coefficients: compute_quotient_polys + coset_ifft (prover.rs:645-789); chunk k
+ *                 of polynomial a (2^log_n coefficients) is quotient polynomial 2a + k (:560-587)
+ *   openings_out  StarkOpeningSet::new (proof.rs:299-334): local_values[C], next_values[C], auxiliary_polys[num_aux],
+ *                 auxiliary_polys_next[num_aux] (2 words each), ctl_zs_first (1 word each), quotient_polys[2 num_challenges]
+ * ctl_challenges = num_challenges x (beta, gamma), alphas = num_challenges words, zeta = 2 words.  Buffers are malloc'ed
+ * (zkm_b200_free). */
+int zkm_b200_stage_table(int system_id, uint32_t table_index, const zkm_table_t* table, const zkm_stark_config_t* cfg,
+                         const uint64_t* ctl_challenges, const uint64_t* alphas, const uint64_t* zeta, uint64_t** aux_out,
+                         uint32_t* num_aux_out, uint64_t** quotient_out, uint64_t** openings_out, size_t* openings_words, char** err);
+
 /* Raw transforms on host buffers (column-major, ncols x 2^log_n), for NTT parity tests.
  * kind: 0 = fft, 1 = ifft, 2 = coset_ifft(7). */
 int zkm_b200_ntt(uint64_t* data, uint32_t ncols, uint32_t log_n, int kind, char** err);

@@ -59,6 +59,9 @@ def load():
     lib.orc_num_ctls.argtypes = [C.c_int]
     lib.orc_lookup_fingerprint.argtypes = [C.c_int, C.c_int, u64, u64p]
     lib.orc_gen_poseidon_rows.argtypes = [u64p, u64p, C.c_size_t, u64p]
+    lib.orc_stage_table.restype = C.c_long
+    lib.orc_stage_table.argtypes = [C.c_int, C.c_uint32, C.POINTER(u64p), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), u64p, u64p, u64p, u64p,
+                                    C.POINTER(C.c_uint32), u64p, u64p]
     lib.orc_hash_pages.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.orc_poseidon_bytes.argtypes = [C.c_char_p, C.c_size_t, u64p]
     lib.orc_const_hash_page.argtypes = [C.c_int, C.c_void_p]
@@ -147,3 +150,23 @@ class OrcPageTree:
         if self.h:
             self.lib.orc_pagetree_destroy(self.h)
             self.h = None
+
+
+def stage_table(lib, system_id, table_index, cols, ctl_challenges, alphas, zeta, cfg=STANDARD_FAST_CONFIG, max_aux=256):
+    """orc_stage_table -> (aux columns (num_aux, n), quotient coefficients (num_challenges, 2n), openings words)."""
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    ncols, n = a.shape
+    nc = cfg[4]
+    cc = np.ascontiguousarray(ctl_challenges, dtype=np.uint64).reshape(-1)
+    al = np.ascontiguousarray(alphas, dtype=np.uint64)
+    ze = np.ascontiguousarray(zeta, dtype=np.uint64)
+    aux = np.zeros(max_aux * n, dtype=np.uint64)
+    quot = np.zeros(nc * 2 * n, dtype=np.uint64)
+    opn = np.zeros(4 * (ncols + max_aux) + max_aux + 4 * nc + 8, dtype=np.uint64)
+    naux = C.c_uint32()
+    cw = (C.c_uint32 * 7)(*cfg)
+    w = lib.orc_stage_table(system_id, table_index, col_ptrs(a), ncols, n.bit_length() - 1, cw, u64ptr(cc), u64ptr(al), u64ptr(ze), u64ptr(aux),
+                            C.byref(naux), u64ptr(quot), u64ptr(opn))
+    if w < 0:
+        raise RuntimeError(lib.orc_last_error().decode())
+    return aux[:naux.value * n].reshape(naux.value, n).copy(), quot.reshape(nc, 2 * n), opn[:w].copy()

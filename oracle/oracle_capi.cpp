@@ -153,6 +153,49 @@ uint64_t* orc_prove_system(int system_id, const uint64_t* const* const* tables, 
         return out;
     } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
 }
+// Stage outputs of prove_single_table for one table under given challenges (the product's zkm_b200_stage_table): auxiliary
+// columns (auxiliary_columns = lookup_helper_columns + cross_table_lookup_data), quotient coefficients (compute_quotient_polys)
+// and StarkOpeningSet::new.  aux_out: num_aux x n, quot_out: num_challenges x 2n, open_out: see include/zkm_b200.h.
+// Returns the number of opening words written, or -1.
+long orc_stage_table(int system_id, uint32_t table_index, const uint64_t* const* cols, uint32_t ncols, uint32_t log_n, const uint32_t* cfg_words,
+                     const uint64_t* ctl_challenges, const uint64_t* alphas_in, const uint64_t* zeta_in, uint64_t* aux_out, uint32_t* num_aux_out,
+                     uint64_t* quot_out, uint64_t* open_out) {
+    try {
+        System sys = zkm::tables::make_system(system_id);
+        StarkConfig cfg = make_cfg(cfg_words);
+        const TableLayout L = zkm::tables::derive_layout(sys, cfg.num_challenges).at(table_index);
+        if ((int)ncols != L.ncols) throw std::runtime_error("wrong number of trace columns");
+        const size_t n = (size_t)1 << log_n;
+        Trace trace(ncols, std::vector<Fp>(n));
+        for (uint32_t c = 0; c < ncols; c++) for (size_t i = 0; i < n; i++) trace[c][i] = Fp(cols[c][i]);
+        std::vector<GrandProductChallenge> chs(cfg.num_challenges);
+        std::vector<Fp> alphas(cfg.num_challenges);
+        for (unsigned k = 0; k < cfg.num_challenges; k++) { chs[k].beta = Fp(ctl_challenges[2 * k]); chs[k].gamma = Fp(ctl_challenges[2 * k + 1]); alphas[k] = Fp(alphas_in[k]); }
+        Trace aux = auxiliary_columns(L, trace, chs);
+        if (aux.empty()) throw std::runtime_error("No CTL?");
+        *num_aux_out = (uint32_t)aux.size();
+        for (size_t c = 0; c < aux.size(); c++) for (size_t i = 0; i < n; i++) aux_out[c * n + i] = aux[c][i].v;
+        PolynomialBatch trace_c = PolynomialBatch::from_values(trace, cfg.fri.rate_bits, cfg.fri.cap_height);
+        PolynomialBatch aux_c = PolynomialBatch::from_values(std::move(aux), cfg.fri.rate_bits, cfg.fri.cap_height);
+        std::vector<std::vector<Fp>> qp = compute_quotient_polys(L, trace_c, aux_c, chs, alphas, log_n, cfg);
+        std::vector<std::vector<Fp>> chunks;
+        for (size_t a = 0; a < qp.size(); a++) {
+            for (size_t i = 0; i < 2 * n; i++) quot_out[a * 2 * n + i] = qp[a][i].v;
+            for (size_t k = 0; k < qp[a].size(); k += n) chunks.emplace_back(qp[a].begin() + k, qp[a].begin() + k + n);
+        }
+        const Ext2 zeta = Ext2(Fp(zeta_in[0]), Fp(zeta_in[1]));
+        const Ext2 zeta_next = zeta * primitive_root_of_unity(log_n);
+        size_t w = 0;
+        auto put_all = [&](const std::vector<std::vector<Fp>>& polys, Ext2 z) {
+            for (auto& p : polys) { Ext2 r = poly_eval_ext(p, z); open_out[w++] = r.a.v; open_out[w++] = r.b.v; }
+        };
+        put_all(trace_c.polynomials, zeta); put_all(trace_c.polynomials, zeta_next);
+        put_all(aux_c.polynomials, zeta); put_all(aux_c.polynomials, zeta_next);
+        for (size_t i = L.num_lookup_cols + L.num_ctl_helpers; i < aux_c.polynomials.size(); i++) open_out[w++] = poly_eval(aux_c.polynomials[i], Fp::one()).v;
+        put_all(chunks, zeta);
+        return (long)w;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 void orc_free(void* p) { free(p); }
 // 0 = accepted, -1 = rejected / malformed (orc_last_error says why).
 int orc_verify_system(int system_id, const uint64_t* proof, size_t words, const uint32_t* cfg_words) {

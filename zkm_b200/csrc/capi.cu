@@ -482,6 +482,45 @@ int zkm_b200_table_from_ops(uint32_t table, const uint64_t* ops, size_t n_ops, u
     ZKM_API_END
 }
 
+int zkm_b200_stage_table(int system_id, uint32_t table_index, const zkm_table_t* table, const zkm_stark_config_t* cfg,
+                         const uint64_t* ctl_challenges, const uint64_t* alphas, const uint64_t* zeta, uint64_t** aux_out, uint32_t* num_aux_out,
+                         uint64_t** quotient_out, uint64_t** openings_out, size_t* openings_words, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(table && table->cols && cfg && ctl_challenges && alphas && zeta && aux_out && num_aux_out && quotient_out && openings_out &&
+              openings_words, "null argument");
+    ZKM_CHECK(table->log_n <= 24 && table->ncols > 0, "bad table shape");
+    Ctx& c = ctx();
+    StarkCfg sc;
+    sc.rate_bits = cfg->rate_bits; sc.cap_height = cfg->cap_height; sc.pow_bits = cfg->pow_bits; sc.num_queries = cfg->num_queries;
+    sc.num_challenges = cfg->num_challenges; sc.arity_bits = cfg->arity_bits; sc.final_poly_bits = cfg->final_poly_bits;
+    ZKM_CHECK(sc.num_challenges >= 1 && sc.num_challenges <= (unsigned)MAX_CHALLENGES, "unsupported num_challenges");
+    AuxChallenges ch = {};
+    ch.count = (int)sc.num_challenges;
+    for (unsigned k = 0; k < sc.num_challenges; k++) {
+        ZKM_CHECK(ctl_challenges[2 * k] < GL_P && ctl_challenges[2 * k + 1] < GL_P && alphas[k] < GL_P, "challenge is not a canonical field element");
+        ch.beta[k] = ctl_challenges[2 * k]; ch.gamma[k] = ctl_challenges[2 * k + 1];
+    }
+    ZKM_CHECK(zeta[0] < GL_P && zeta[1] < GL_P, "challenge is not a canonical field element");
+    const size_t n = (size_t)1 << table->log_n;
+    DevBuf values((size_t)table->ncols * n, c.stream);
+    for (uint32_t i = 0; i < table->ncols; i++) {
+        ZKM_CHECK(table->cols[i], "null column pointer");
+        values.upload(table->cols[i], n, (size_t)i * n);
+    }
+    std::vector<u64> aux, quot, open;
+    stage_single_table(system_id, (int)table_index, sc, std::move(values), (int)table->ncols, (int)table->log_n, ch, alphas,
+                       gl2(gl(zeta[0]), gl(zeta[1])), aux, quot, open);
+    auto dup = [](const std::vector<u64>& v) {
+        uint64_t* p = (uint64_t*)malloc(std::max<size_t>(1, v.size()) * sizeof(u64));
+        ZKM_CHECK(p, "out of host memory");
+        memcpy(p, v.data(), v.size() * sizeof(u64));
+        return p;
+    };
+    *aux_out = dup(aux); *num_aux_out = (uint32_t)(aux.size() / n);
+    *quotient_out = dup(quot); *openings_out = dup(open); *openings_words = open.size();
+    ZKM_API_END
+}
+
 int zkm_b200_memory_trace(const uint64_t* ops, size_t n_ops, uint64_t** cols_out, uint32_t* log_n_out, char** err) {
     ZKM_API_BEGIN
     ZKM_CHECK(ops && cols_out && log_n_out, "null argument");

@@ -394,6 +394,67 @@ static void prove_single_table(TableJob& job, const StarkCfg& cfg, const AuxChal
     pt.mark("serialise");
 }
 
+// Stage-by-stage outputs of prove_single_table for ONE table of a System under caller-given challenges (no transcript): what
+// SURVEY section 8(b) calls the finer-grained seam (cross_table_lookup_data + lookup_helper_columns, compute_quotient_polys +
+// post-processing, StarkOpeningSet::new), for stage-level parity tests against the oracle.
+void stage_single_table(int system_id, int table_index, const StarkCfg& cfg, DevBuf&& values, int ncols, int log_n, const AuxChallenges& ctl_ch,
+                        const u64* alphas, gl2 zeta, std::vector<u64>& aux_out, std::vector<u64>& quot_out, std::vector<u64>& open_out) {
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    tables::System sys = tables::make_system(system_id);
+    ZKM_CHECK(table_index >= 0 && (size_t)table_index < sys.kinds.size(), "no such table in this system");
+    ZKM_CHECK(cfg.num_challenges >= 1 && cfg.num_challenges <= MAX_CHALLENGES && ctl_ch.count == (int)cfg.num_challenges, "unsupported num_challenges");
+    ZKM_CHECK(cfg.rate_bits == 2, "only rate_bits = 2 is supported (quotient kernel layout)");
+    const tables::TableLayout L = tables::derive_layout(sys, cfg.num_challenges)[table_index];
+    const int kind = sys.kinds[table_index], na = cfg.num_challenges;
+    ZKM_CHECK(ncols == L.ncols, "wrong number of trace columns");
+    ZKM_CHECK(log_n + (int)cfg.rate_bits >= (int)cfg.cap_height && log_n >= 1, "trace too short");
+    const size_t n = (size_t)1 << log_n;
+    Batch trace;
+    {
+        DevBuf coeffs((size_t)ncols * n, s);
+        ntt_inverse(c.ntt, values.p, n, coeffs.p, n, ncols, log_n, s);
+        batch_from_coeffs_dev(trace, std::move(coeffs), ncols, log_n, cfg.rate_bits, cfg.cap_height);
+    }
+    DProgram prog;
+    prog.build(L, na);
+    prog.upload(s);
+    const int naux = L.num_aux();
+    ZKM_CHECK(naux > 0, "No CTL?");
+    Batch aux;
+    {
+        DevBuf auxv((size_t)naux * n, s);
+        compute_aux_columns(prog, L, values.p, log_n, ctl_ch, auxv.p, s);
+        aux_out.resize((size_t)naux * n);
+        auxv.download(aux_out.data(), aux_out.size());
+        batch_from_values_dev(aux, std::move(auxv), naux, log_n, cfg.rate_bits, cfg.cap_height);
+    }
+    Batch quot;
+    {
+        DevBuf q((size_t)na * 2 * n, s);
+        compute_quotient_values(kind, prog, L, trace, aux, ctl_ch, alphas, na, q.p, s);
+        coset_intt(c.ntt, q.p, 2 * n, q.p, 2 * n, na, log_n + 1, s);
+        quot_out.resize((size_t)na * 2 * n);
+        q.download(quot_out.data(), quot_out.size());
+        batch_from_coeffs_dev(quot, std::move(q), 2 * na, log_n, cfg.rate_bits, cfg.cap_height);
+    }
+    ZKM_CHECK(gl2_exp2(zeta, log_n) != gl2::one(), "Opening point is in the subgroup.");
+    const gl2 zeta_next = zeta * gl_root_of_unity(log_n);
+    const int C = L.ncols, Q = 2 * na, zstart = L.num_lookup_cols + L.num_ctl_helpers;
+    gl2 pts[3] = {zeta, zeta_next, gl2::one()};
+    std::vector<u64> h((size_t)std::max(std::max(C, naux), Q) * 3 * 2);
+    // layout of open_out: local[C], next[C], aux[naux], aux_next[naux] (2 words each), ctl_zs_first (1 word each), quot[Q] (2 words)
+    open_out.clear();
+    eval_polys_at_points(trace.coeffs.p, C, log_n, pts, 2, h.data(), s);
+    for (int p = 0; p < 2; p++) for (int i = 0; i < C; i++) { open_out.push_back(h[(i * 2 + p) * 2]); open_out.push_back(h[(i * 2 + p) * 2 + 1]); }
+    eval_polys_at_points(aux.coeffs.p, naux, log_n, pts, 3, h.data(), s);
+    for (int p = 0; p < 2; p++) for (int i = 0; i < naux; i++) { open_out.push_back(h[(i * 3 + p) * 2]); open_out.push_back(h[(i * 3 + p) * 2 + 1]); }
+    for (int i = zstart; i < naux; i++) open_out.push_back(h[(i * 3 + 2) * 2]);
+    eval_polys_at_points(quot.coeffs.p, Q, log_n, pts, 1, h.data(), s);
+    for (int i = 0; i < Q; i++) { open_out.push_back(h[i * 2]); open_out.push_back(h[i * 2 + 1]); }
+    ZKM_CUDA(cudaStreamSynchronize(s));
+}
+
 std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<TableInput>& inputs, const PublicInputs& pv) {
     Ctx& c = ctx();
     cudaStream_t s = c.stream;

@@ -38,4 +38,8 @@ inline std::vector<size_t> commit_order(const std::vector<size_t>& sizes) {
 // Returns the proof in the flat u64 layout documented in include/zkm_b200.h.
 std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<TableInput>& inputs, const PublicInputs& pv);
 
+// One table's stage outputs under given challenges (prover.cu): auxiliary columns, quotient coefficients, openings.
+void stage_single_table(int system_id, int table_index, const StarkCfg& cfg, DevBuf&& values, int ncols, int log_n, const AuxChallenges& ctl_ch,
+                        const u64* alphas, gl2 zeta, std::vector<u64>& aux_out, std::vector<u64>& quot_out, std::vector<u64>& open_out);
+
 }  // namespace zkm

@@ -37,7 +37,7 @@ EXPORTS = [
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
-    "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
+    "zkm_b200_stage_table", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
 ]
 
 
@@ -440,3 +440,27 @@ class PageTree:
         if self.h:
             self.lib.zkm_b200_pagetree_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def stage_table(lib, system_id: int, table_index: int, cols, ctl_challenges, alphas, zeta, cfg=None):
+    """zkm_b200_stage_table -> (aux columns (num_aux, n), quotient coefficients (num_challenges, 2n), openings words)."""
+    cfg = cfg or standard_fast_config(lib)
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    t, keep = make_table(a)
+    cc = np.ascontiguousarray(ctl_challenges, dtype=np.uint64).reshape(-1)
+    al = np.ascontiguousarray(alphas, dtype=np.uint64)
+    ze = np.ascontiguousarray(zeta, dtype=np.uint64)
+    aux, quot, opn = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+    naux, words, err = C.c_uint32(), C.c_size_t(), C.c_void_p()
+    u64p = C.POINTER(C.c_uint64)
+    lib.zkm_b200_stage_table.argtypes = [C.c_int, C.c_uint32, C.POINTER(Table), C.POINTER(StarkConfig), u64p, u64p, u64p, C.POINTER(u64p),
+                                         C.POINTER(C.c_uint32), C.POINTER(u64p), C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    check(lib, lib.zkm_b200_stage_table(system_id, table_index, C.byref(t), C.byref(cfg), u64ptr(cc), u64ptr(al), u64ptr(ze), C.byref(aux),
+                                        C.byref(naux), C.byref(quot), C.byref(opn), C.byref(words), C.byref(err)), err)
+    n, nc = a.shape[1], cfg.num_challenges
+    out = (np.ctypeslib.as_array(aux, shape=(naux.value * n,)).copy().reshape(naux.value, n),
+           np.ctypeslib.as_array(quot, shape=(nc * 2 * n,)).copy().reshape(nc, 2 * n),
+           np.ctypeslib.as_array(opn, shape=(words.value,)).copy())
+    for p in (aux, quot, opn):
+        lib.zkm_b200_free(p)
+    return out

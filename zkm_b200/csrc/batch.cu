@@ -109,6 +109,12 @@ Ctx& ctx() {
     if (!g_ctx) throw std::runtime_error("zkm_b200: not initialised (call zkm_b200_init; a CUDA device is required)");
     return *g_ctx;
 }
+Ctx::~Ctx() {
+    for (int k = 0; k < BOUNCE_SLOTS; k++) {
+        if (bounce_free[k]) cudaEventDestroy(bounce_free[k]);
+        if (bounce[k]) cudaFreeHost(bounce[k]);
+    }
+}
 void ctx_init(int device) {
     if (g_ctx) return;
     int count = 0;

@@ -17,6 +17,15 @@ struct Ctx {
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = 0;          // host->device trace uploads, overlapped with the commitments
     NttTables ntt;
+    // Pinned bounce ring for host->device copies from PAGEABLE memory (the real caller's `Vec<F>` columns): the uploader copies
+    // chunk k into slot k % BOUNCE_SLOTS with a few host threads while the DMA engine drains the previous slots, instead of the
+    // driver's own serial stage-then-copy.  Allocated on first use (upload_bounced, capi.cu), released with the context.
+    static constexpr int BOUNCE_SLOTS = 4;
+    static constexpr size_t BOUNCE_BYTES = (size_t)16 << 20;
+    void* bounce[BOUNCE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t bounce_free[BOUNCE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    int bounce_next = 0;
+    ~Ctx();
 };
 Ctx& ctx();                    // throws if zkm_b200_init has not succeeded
 bool ctx_ready();

@@ -220,6 +220,46 @@ static size_t table_from_ops_dev(int table, const u64* ops, size_t n_ops, size_t
     }
 }
 
+// Host -> device copy of `bytes` from `src` on stream `cs`.  Pinned (or registered) sources go straight to cudaMemcpyAsync.
+// Pageable sources -- what a `Vec<F>` column of the reference is -- go through the context's pinned bounce ring: the chunk is
+// copied into a free slot by up to 4 host threads while the DMA engine is still draining the previous slots (the driver's own
+// pageable path stages and copies serially on the calling thread: 7.4 GB/s end to end on the bench host against 9.2 needed).
+// ZKM_BOUNCE=0 switches the ring off (A/B).
+static bool source_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static cudaError_t upload_bounced(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t cs) {
+    static const bool enabled = !(std::getenv("ZKM_BOUNCE") && atoi(std::getenv("ZKM_BOUNCE")) == 0);
+    if (!enabled || bytes < ((size_t)1 << 20) || !source_is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs);
+    for (size_t off = 0; off < bytes;) {
+        const size_t len = std::min(bytes - off, Ctx::BOUNCE_BYTES);
+        const int k = c->bounce_next;
+        c->bounce_next = (k + 1) % Ctx::BOUNCE_SLOTS;
+        cudaError_t e;
+        if (!c->bounce[k]) {
+            if ((e = cudaHostAlloc(&c->bounce[k], Ctx::BOUNCE_BYTES, cudaHostAllocDefault)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&c->bounce_free[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+        } else if ((e = cudaEventSynchronize(c->bounce_free[k])) != cudaSuccess) return e;      // the slot's last DMA has finished
+        const char* from = (const char*)src + off;
+        char* slot = (char*)c->bounce[k];
+        const int parts = len >= ((size_t)4 << 20) ? 4 : 1;
+        const size_t per = (len / parts + 63) & ~(size_t)63;
+        std::thread helpers[3];
+        for (int t = 1; t < parts; t++) {
+            const size_t b = std::min(len, (size_t)t * per), e2 = std::min(len, (size_t)(t + 1) * per);
+            helpers[t - 1] = std::thread([=] { memcpy(slot + b, from + b, e2 - b); });
+        }
+        memcpy(slot, from, std::min(len, per));
+        for (int t = 1; t < parts; t++) helpers[t - 1].join();
+        if ((e = cudaMemcpyAsync((char*)dst + off, slot, len, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(c->bounce_free[k], cs)) != cudaSuccess) return e;
+        off += len;
+    }
+    return cudaSuccess;
+}
+
 static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t num_tables, const uint64_t* const* d_tables,
                         const uint32_t* roots_before, const uint32_t* roots_after, const uint8_t* userdata, uint32_t userdata_len,
                         const zkm_stark_config_t* cfg, uint64_t** proof_out, size_t* proof_words,
@@ -332,7 +372,8 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
         // builds them after the transposition, :127-153): they are generated on the device
         const int arith_rows_table = (system_id == tables::SYSTEM_ALL_STARK && rows_src[tables::T_ARITHMETIC]) ? tables::T_ARITHMETIC : -1;
         unsigned* d_bad = (unsigned*)bad_flag.p;
-        up.th = std::thread([&up, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage, arith_rows_table, d_bad] {
+        Ctx* cptr = &c;
+        up.th = std::thread([&up, cptr, tables, num_tables, device, cs, dst, evs, order, gends, gevs, rows_src, rows_stage, arith_rows_table, d_bad] {
             cudaSetDevice(device);
             for (size_t t : order) {
                 if (!evs[t]) continue;                      // generated on the device: nothing to upload
@@ -341,7 +382,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                 size_t g = 0;
                 if (rows_src[t]) {
                     // rows as generated (one contiguous block), transposed into column-major on the device
-                    e = cudaMemcpyAsync(rows_stage[t], rows_src[t], (size_t)tables[t].ncols * n * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                    e = upload_bounced(cptr, rows_stage[t], rows_src[t], (size_t)tables[t].ncols * n * sizeof(u64), cs);
                     if (e == cudaSuccess) {
                         try {
                             transpose_rows_to_cols(rows_stage[t], dst[t], n, (int)tables[t].ncols, cs);
@@ -373,7 +414,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                     if (e == cudaSuccess) e = cudaStreamSynchronize(cs);      // `pack` is released at the end of this scope
                 } else
                 for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++) {
-                    e = cudaMemcpyAsync(dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cudaMemcpyHostToDevice, cs);
+                    e = upload_bounced(cptr, dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cs);
                     if (e == cudaSuccess && g < gends[t].size() && (int)i + 1 == gends[t][g]) {
                         e = cudaEventRecord(gevs[t][g], cs);
                         g++;

@@ -232,6 +232,24 @@ int zkm_b200_prove_system_device(int system_id, const zkm_table_t* shapes, const
 int zkm_b200_proof_table_json(const uint64_t* proof, size_t proof_words, uint32_t table, char** json_out, size_t* json_len, char** err);
 int zkm_b200_public_values_json(const uint64_t* proof, size_t proof_words, char** json_out, size_t* json_len, char** err);
 
+/* The segment file: `serde_json::to_vec(&segment)` for the emulator's `Segment` (emulator/src/state.rs:33-48; written by
+ * split_segment :1498-1503, read back by prove_segments).  mem_image is given as the pages the segment read (Memory::rtrace,
+ * memory.rs:524-538 get_input_image): n_pages pages of 4096 bytes with strictly ascending page indices (address >> 12); the
+ * text lists every word, key = address (decimal string, BTreeMap order), value = u32::from_le_bytes of the page bytes.
+ * Host-only.  The string is malloc'ed (zkm_b200_free_string). */
+typedef struct {
+    const uint32_t* page_indices; const uint8_t* pages; size_t n_pages;
+    uint32_t pc, segment_id;
+    uint8_t pre_image_id[32], pre_hash_root[32], image_id[32], page_hash_root[32];
+    uint32_t end_pc;
+    uint64_t step;
+    const uint8_t* const* input_stream; const size_t* input_stream_lens; size_t n_input_streams;
+    uint64_t input_stream_ptr;
+    const uint8_t* public_values_stream; size_t public_values_stream_len;
+    uint64_t public_values_stream_ptr;
+} zkm_segment_t;
+int zkm_b200_segment_json(const zkm_segment_t* seg, char** json_out, size_t* json_len, char** err);
+
 /* ---- emulator segment splitter: page hashes and image id ---------------------------------------
  *
  * At every segment boundary the reference's InstrumentedState::split_segment (emulator/src/state.rs:1460-1530) calls

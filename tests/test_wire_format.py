@@ -93,3 +93,32 @@ def test_json_errors():
     assert lib.zkm_b200_proof_table_json(zl.u64ptr(bad), bad.size, 0, C.byref(out), C.byref(n), C.byref(err)) == -1
     assert b"magic" in C.cast(err, C.c_char_p).value
     lib.zkm_b200_free_string(err)
+
+
+def test_segment_json_is_the_serde_text_of_the_emulator_segment():
+    """zkm_b200_segment_json against Python's own compact JSON of the same structure (emulator/src/state.rs:33-48: field order of
+    the struct, BTreeMap<u32, u32> as an object with decimal-string keys in ascending numeric order, [u8; 32] and Vec<u8> as
+    arrays of numbers), and the reference's get_input_image word order (memory.rs:524-538)."""
+    lib = zl.load()
+    rng = np.random.default_rng(8)
+    idx = [3, 0x10, 0x7FFFD, 0x81020]
+    pages = rng.integers(0, 256, size=(len(idx), 4096), dtype=np.uint8)
+    pages[1] = 0
+    ids = [bytes(int(b) for b in rng.integers(0, 256, size=32)) for _ in range(4)]
+    streams = [b"", bytes(range(5)), bytes([255, 0, 7])]
+    pvs = bytes(range(40))
+    text = zl.segment_json(lib, idx, pages, 0x1234, 7, ids[0], ids[1], ids[2], ids[3], 0xFFFF0000, (1 << 40) + 5, streams, 2, pvs, 40)
+    image = {}
+    for k, pi in enumerate(idx):
+        for i in range(1024):
+            image[str((pi << 12) + 4 * i)] = int.from_bytes(pages[k, 4 * i:4 * i + 4].tobytes(), "little")
+    want = {"mem_image": image, "pc": 0x1234, "segment_id": 7, "pre_image_id": list(ids[0]), "pre_hash_root": list(ids[1]), "image_id": list(ids[2]),
+            "page_hash_root": list(ids[3]), "end_pc": 0xFFFF0000, "step": (1 << 40) + 5, "input_stream": [list(b) for b in streams], "input_stream_ptr": 2,
+            "public_values_stream": list(pvs), "public_values_stream_ptr": 40}
+    assert text.decode() == json.dumps(want, separators=(",", ":"))
+    assert list(json.loads(text)["mem_image"].keys())[:2] == [str(3 << 12), str((3 << 12) + 4)]
+    import pytest
+    with pytest.raises(zl.ZkmError, match="ascending"):
+        zl.segment_json(lib, [5, 5], pages[:2], 0, 0, ids[0], ids[1], ids[2], ids[3], 0, 0, [], 0, b"", 0)
+    empty = zl.segment_json(lib, [], np.zeros((0, 4096), dtype=np.uint8), 1, 2, ids[0], ids[1], ids[2], ids[3], 3, 4, [], 0, b"", 0)
+    assert json.loads(empty)["mem_image"] == {} and json.loads(empty)["input_stream"] == []

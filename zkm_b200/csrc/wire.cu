@@ -186,4 +186,56 @@ int zkm_b200_public_values_json(const uint64_t* proof, size_t proof_words, char*
     return 0;
 }
 
+// Segment (emulator/src/state.rs:33-48, #[derive(Serialize)]): the file split_segment writes per segment (:1498-1503) and
+// `prove_segments` reads back (prover/examples/utils/src/utils.rs).  mem_image is get_input_image (memory.rs:524-538): every
+// word of every page the segment read, keyed by address, value = u32::from_le_bytes of the page bytes; a BTreeMap<u32, u32>
+// serialises as an object with decimal string keys in ascending key order.
+int zkm_b200_segment_json(const zkm_segment_t* seg, char** json_out, size_t* json_len, char** err) {
+    if (err) *err = nullptr;
+    try {
+        ZKM_CHECK(seg && json_out, "null argument");
+        ZKM_CHECK((seg->page_indices && seg->pages) || seg->n_pages == 0, "null pages");
+        Js j;
+        j.s.reserve(64 + seg->n_pages * 4096 * 6);
+        j.s += '{';
+        j.key("mem_image"); j.s += '{';
+        bool first = true;
+        for (size_t k = 0; k < seg->n_pages; k++) {
+            ZKM_CHECK(k == 0 || seg->page_indices[k] > seg->page_indices[k - 1], "page indices must be strictly ascending (BTreeMap order)");
+            ZKM_CHECK(seg->page_indices[k] < (1u << 20), "page index out of range");
+            const uint8_t* pg = seg->pages + k * 4096;
+            for (uint32_t i = 0; i < 1024; i++) {
+                uint32_t w; memcpy(&w, pg + 4 * i, 4);
+                if (!first) j.s += ',';
+                first = false;
+                j.s += '"'; j.num(((u64)seg->page_indices[k] << 12) + 4 * i); j.s += "\":"; j.num(w);
+            }
+        }
+        j.s += '}';
+        auto bytes32 = [&](const char* name, const uint8_t* b) { j.s += ','; j.key(name); j.list(32, [&](size_t i) { j.num(b[i]); }); };
+        j.s += ','; j.key("pc"); j.num(seg->pc);
+        j.s += ','; j.key("segment_id"); j.num(seg->segment_id);
+        bytes32("pre_image_id", seg->pre_image_id); bytes32("pre_hash_root", seg->pre_hash_root);
+        bytes32("image_id", seg->image_id); bytes32("page_hash_root", seg->page_hash_root);
+        j.s += ','; j.key("end_pc"); j.num(seg->end_pc);
+        j.s += ','; j.key("step"); j.num(seg->step);
+        j.s += ','; j.key("input_stream");
+        ZKM_CHECK((seg->input_stream && seg->input_stream_lens) || seg->n_input_streams == 0, "null input stream");
+        j.list(seg->n_input_streams, [&](size_t k) {
+            const uint8_t* b = seg->input_stream[k];
+            ZKM_CHECK(b || seg->input_stream_lens[k] == 0, "null input stream");
+            j.list(seg->input_stream_lens[k], [&](size_t i) { j.num(b[i]); });
+        });
+        j.s += ','; j.key("input_stream_ptr"); j.num(seg->input_stream_ptr);
+        j.s += ','; j.key("public_values_stream");
+        ZKM_CHECK(seg->public_values_stream || seg->public_values_stream_len == 0, "null public values stream");
+        j.list(seg->public_values_stream_len, [&](size_t i) { j.num(seg->public_values_stream[i]); });
+        j.s += ','; j.key("public_values_stream_ptr"); j.num(seg->public_values_stream_ptr);
+        j.s += '}';
+        if (json_len) *json_len = j.s.size();
+        *json_out = dup(j.s);
+    } catch (const std::exception& e) { return fail(err, e); }
+    return 0;
+}
+
 }  // extern "C"

@@ -37,7 +37,7 @@ EXPORTS = [
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
-    "zkm_b200_stage_table", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
+    "zkm_b200_stage_table", "zkm_b200_segment_json", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
 ]
 
 
@@ -464,3 +464,35 @@ def stage_table(lib, system_id: int, table_index: int, cols, ctl_challenges, alp
     for p in (aux, quot, opn):
         lib.zkm_b200_free(p)
     return out
+
+
+class SegmentC(C.Structure):
+    _fields_ = [("page_indices", C.POINTER(C.c_uint32)), ("pages", C.c_void_p), ("n_pages", C.c_size_t), ("pc", C.c_uint32),
+                ("segment_id", C.c_uint32), ("pre_image_id", C.c_uint8 * 32), ("pre_hash_root", C.c_uint8 * 32), ("image_id", C.c_uint8 * 32),
+                ("page_hash_root", C.c_uint8 * 32), ("end_pc", C.c_uint32), ("step", C.c_uint64), ("input_stream", C.POINTER(C.c_char_p)),
+                ("input_stream_lens", C.POINTER(C.c_size_t)), ("n_input_streams", C.c_size_t), ("input_stream_ptr", C.c_uint64),
+                ("public_values_stream", C.c_char_p), ("public_values_stream_len", C.c_size_t), ("public_values_stream_ptr", C.c_uint64)]
+
+
+def segment_json(lib, page_indices, pages, pc, segment_id, pre_image_id, pre_hash_root, image_id, page_hash_root, end_pc, step, input_stream,
+                 input_stream_ptr, public_values_stream, public_values_stream_ptr) -> bytes:
+    """zkm_b200_segment_json: the emulator's Segment file (serde_json).  Host-only."""
+    idx = np.ascontiguousarray(page_indices, dtype=np.uint32)
+    pg = np.ascontiguousarray(pages, dtype=np.uint8).reshape(-1, 4096)
+    s = SegmentC()
+    s.page_indices, s.pages, s.n_pages = idx.ctypes.data_as(C.POINTER(C.c_uint32)), pg.ctypes.data, idx.size
+    s.pc, s.segment_id, s.end_pc, s.step = pc, segment_id, end_pc, step
+    for name, val in (("pre_image_id", pre_image_id), ("pre_hash_root", pre_hash_root), ("image_id", image_id), ("page_hash_root", page_hash_root)):
+        setattr(s, name, (C.c_uint8 * 32)(*val))
+    streams = [bytes(b) for b in input_stream]
+    arr = (C.c_char_p * max(1, len(streams)))(*streams)
+    lens = (C.c_size_t * max(1, len(streams)))(*[len(b) for b in streams])
+    s.input_stream, s.input_stream_lens, s.n_input_streams, s.input_stream_ptr = arr, lens, len(streams), input_stream_ptr
+    pvs = bytes(public_values_stream)
+    s.public_values_stream, s.public_values_stream_len, s.public_values_stream_ptr = pvs, len(pvs), public_values_stream_ptr
+    out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+    lib.zkm_b200_segment_json.argtypes = [C.POINTER(SegmentC), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    check(lib, lib.zkm_b200_segment_json(C.byref(s), C.byref(out), C.byref(n), C.byref(err)), err)
+    text = C.string_at(out, n.value)
+    lib.zkm_b200_free_string(out)
+    return text

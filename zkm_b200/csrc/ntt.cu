@@ -50,8 +50,13 @@ struct NttPassParams {
     int ncols_total;              // valid range for the "t = column" single-pass mode
     int t_is_column;              // single-pass mode: t indexes columns; guard against ncols
     int load_t_fast, store_t_fast;
-    PowTable pre[8]; int has_pre; size_t pre_b, pre_r, pre_t;     // input scale  pre[z]^(b*pre_b+r*pre_r+t*pre_t)
-    PowTable post; int has_post; size_t post_b, post_t;           // output scale post^((b*post_b+t*post_t)*k)
+    PowTable pre[8]; int has_pre; size_t pre_b, pre_r, pre_t;     // has_pre = 1: input scale  pre[z]^(b*pre_b+r*pre_r+t*pre_t)
+    PowTable post; int has_post; size_t post_b, post_t;           // has_post = 1: output scale post^((b*post_b+t*post_t)*k)
+    // Full-size factor tables of the two-pass transforms (has_pre / has_post = 2, FullTables below): the input is scaled by
+    // pre_row[z][r] (the row part of the coset shift), the output by post_full[z][position inside the column] -- the inter-pass
+    // twiddle times the column part of the coset shift times the constant output factor, ONE load + ONE multiply per element
+    // where the two-level power tables cost two loads + two multiplies at each end.
+    const u64* pre_row[8]; const u64* post_full[8];
     u64 scale;                    // constant output multiplier (1 = none)
     const u64* tw;                // w_R^k, k < R/2
 };
@@ -163,7 +168,9 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 phase) {
     } while (!done);
 }
 
-template <int LOG_R>
+// FT: the launch uses the full-size factor tables (has_pre in {0, 2}, has_post = 2) -- a compile-time variant, so that neither
+// path pays for the other's branches.
+template <int LOG_R, bool FT>
 __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams p) {
     constexpr int R = 1 << LOG_R;
     extern __shared__ __align__(16) u64 smem[];
@@ -194,7 +201,9 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams
         u64 v = 0;
         if (t < tmax) {
             v = in[(size_t)r * p.in_r + (size_t)t * p.in_t];
-            if (p.has_pre) {
+            if (FT) {
+                if (p.has_pre) v = fmul(gl(v), gl(__ldg(p.pre_row[z] + r))).v;
+            } else if (p.has_pre) {
                 u64 e = b * p.pre_b + (size_t)r * p.pre_r + (size_t)t * p.pre_t;
                 v = fmul(gl(v), pow_lookup(p.pre[z], e)).v;
             }
@@ -207,6 +216,19 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams
     radix_steps<LOG_R>(x, tw, p, log_T, tid, nth);
     // ---- store ----
     const gl scale(p.scale);
+    if (FT) {
+        // pass A of a two-pass transform: k-major tile (store_t_fast), every t valid; the factor loads of four elements are issued
+        // together ahead of their multiplies
+        const u64* __restrict__ ftab = p.post_full[z] + b * p.out_b;
+#pragma unroll 4
+        for (int idx = tid; idx < total; idx += nth) {
+            const int k = idx >> log_T, t = idx & (T - 1);
+            const size_t o = (size_t)k * p.out_r + (size_t)t * p.out_t;
+            const gl f(__ldg(ftab + o));
+            out[o] = fmul(gl(x[freq_position<LOG_R>(k) * TS + t]), f).v;
+        }
+        return;
+    }
     for (int idx = tid; idx < total; idx += nth) {
         int k, t;
         if (p.store_t_fast) { k = idx >> log_T; t = idx & (T - 1); } else { t = idx >> LOG_R; k = idx & (R - 1); }
@@ -222,9 +244,9 @@ __global__ void __launch_bounds__(NTT_MAX_THREADS) ntt_pass_kernel(NttPassParams
 }
 
 typedef void (*ntt_kernel_t)(NttPassParams);
-static ntt_kernel_t kernel_for(int log_r) {
+static ntt_kernel_t kernel_for(int log_r, bool ft) {
     switch (log_r) {
-#define K(i) case i: return ntt_pass_kernel<i>;
+#define K(i) case i: return ft ? ntt_pass_kernel<i, true> : ntt_pass_kernel<i, false>;
         K(0) K(1) K(2) K(3) K(4) K(5) K(6) K(7) K(8) K(9) K(10) K(11) K(12)
 #undef K
     }
@@ -237,7 +259,7 @@ static void launch_pass(int log_r, NttPassParams p, dim3 grid, cudaStream_t s, d
     while ((1 << p.log_T) < p.T) p.log_T++;
     ZKM_CHECK((1 << p.log_T) == p.T, "NTT tile width must be a power of two");
     size_t smem = (R + R * (p.T + 1)) * sizeof(u64);
-    ntt_kernel_t k = kernel_for(log_r);
+    ntt_kernel_t k = kernel_for(log_r, p.has_post == 2);
     // alg_bytes: this launch's share of the transform's algorithmic bytes (inputs read once, outputs
     // written once -- charged to the first pass); the second counter is the traffic of the pass itself, 16 B per element
     ProfScope ps("ntt_pass", s, alg_bytes, 16.0 * (double)R * p.T * grid.x * grid.y * grid.z);
@@ -262,6 +284,9 @@ struct NttTables::Impl {
     std::map<std::pair<int, int>, std::shared_ptr<DevBuf>> tw;
     // coset shift tables: key (log_n, rate_bits, j, inverse, shift_exp_bits)
     std::map<std::tuple<int, int, int, int, int>, std::shared_ptr<PowTableOwner>> shifts;
+    // full-size factor tables of the two-pass transforms: key (log_n, inverse, rate_bits, j, shift_exp_bits; rate_bits = -1: no shift)
+    struct FullTab { DevBuf row, full; };
+    std::map<std::tuple<int, int, int, int, int>, std::shared_ptr<FullTab>> full;
 };
 NttTables::NttTables() : impl(new Impl) {}
 NttTables::~NttTables() { delete impl; }
@@ -309,6 +334,50 @@ static std::shared_ptr<PowTableOwner> get_shift(NttTables& T, int log_n, int rat
     return t;
 }
 
+// full[k1 * n2 + i2] = w_n^(i2 k1) * shift^i2 * scale   (inter-pass twiddle x column part of the coset shift x constant);
+// row[r] = shift^(r n2)   (row part of the coset shift).  Field arithmetic is exact: the transforms give the same words.
+__global__ void build_full_table_kernel(u64* full, u64* row, int l1, int l2, PowTable roots, PowTable shift, int has_shift, u64 scale) {
+    const size_t n1 = (size_t)1 << l1, n2 = (size_t)1 << l2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n1 * n2) return;
+    const size_t k1 = idx >> l2, i2 = idx & (n2 - 1);
+    gl v = pow_lookup(roots, (u64)i2 * k1);
+    if (has_shift) v = v * pow_lookup(shift, i2);
+    if (scale != 1) v = v * gl(scale);
+    full[idx] = v.v;
+    if (has_shift && idx < n1) row[idx] = pow_lookup(shift, (u64)idx * n2).v;
+}
+static void plan(int log_n, int& l1, int& l2, int& T);
+struct ShiftKey { int rate_bits, j, shift_exp_bits; };               // coset shift 7^(2^shift_exp_bits) * w_{n 2^rate_bits}^j
+static std::shared_ptr<NttTables::Impl::FullTab> get_full(NttTables& T, int log_n, int inverse, const ShiftKey* sk, u64 scale, cudaStream_t s) {
+    auto key = sk ? std::make_tuple(log_n, inverse, sk->rate_bits, sk->j, sk->shift_exp_bits) : std::make_tuple(log_n, inverse, -1, 0, 0);
+    {
+        std::lock_guard<std::mutex> g(T.impl->mu);
+        auto it = T.impl->full.find(key);
+        if (it != T.impl->full.end()) return it->second;
+    }
+    int l1, l2, tw;
+    plan(log_n, l1, l2, tw);
+    auto roots = get_roots(T, log_n, inverse, s);
+    std::shared_ptr<PowTableOwner> sh;
+    if (sk) sh = get_shift(T, log_n, sk->rate_bits, sk->j, 0, s, sk->shift_exp_bits);
+    auto t = std::make_shared<NttTables::Impl::FullTab>();
+    const size_t n = (size_t)1 << log_n;
+    t->full.alloc(n, s);
+    t->row.alloc((size_t)1 << l1, s);
+    build_full_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t->full.p, t->row.p, l1, l2, roots->view, sk ? sh->view : roots->view, sk != nullptr, scale);
+    ZKM_LAUNCHED();
+    ZKM_CUDA(cudaStreamSynchronize(s));
+    std::lock_guard<std::mutex> g(T.impl->mu);
+    T.impl->full[key] = t;
+    return t;
+}
+// ZKM_NTT_FULLTAB=0 falls back to the two-level power tables on both ends of pass A (A/B switch)
+static bool use_full_tables() {
+    static const bool on = !(std::getenv("ZKM_NTT_FULLTAB") && atoi(std::getenv("ZKM_NTT_FULLTAB")) == 0);
+    return on;
+}
+
 // Split log_n into (log_n1, log_n2) and choose the tile width.
 static void plan(int log_n, int& l1, int& l2, int& T) {
     if (log_n <= 12) { l1 = log_n; l2 = 0; T = (1 << 12) >> log_n; if (T > 16) T = 16; if (T < 1) T = 1; return; }
@@ -325,7 +394,7 @@ static void plan(int log_n, int& l1, int& l2, int& T) {
 // alg_bytes_per_col: algorithmic bytes of the whole call per column.
 static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_zs, u64* out, size_t out_cs, size_t out_zs,
                         int ncols, int nz, int log_n, int inverse, const PowTable* pre, u64 final_scale, cudaStream_t s,
-                        double alg_bytes_per_col) {
+                        double alg_bytes_per_col, const ShiftKey* shift_keys = nullptr) {
     if (ncols == 0) return;
     int l1, l2, T;
     plan(log_n, l1, l2, T);
@@ -355,6 +424,11 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
     }
     size_t n1 = (size_t)1 << l1, n2 = (size_t)1 << l2;
     auto roots = get_roots(tabs, log_n, inverse, s);
+    // full-size factor tables (one load + one multiply per element at each end of pass A; the constant output factor rides along)
+    const bool fulltab = use_full_tables() && (!pre || shift_keys);
+    std::shared_ptr<NttTables::Impl::FullTab> ft[8];
+    if (fulltab)
+        for (int z = 0; z < nz; z++) ft[z] = get_full(tabs, log_n, inverse, pre ? &shift_keys[z] : nullptr, final_scale, s);
     const u64* twA = get_tw(tabs, l1, inverse, s);
     const u64* twB = get_tw(tabs, l2, inverse, s);
     // Column chunks sized so the inter-pass scratch (pass A output) stays L2-resident (~64 MB).
@@ -374,6 +448,11 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         p.pre_b = T; p.pre_r = n2; p.pre_t = 1;
         p.post = roots->view; p.has_post = 1; p.post_b = T; p.post_t = 1;
         p.scale = 1;
+        if (fulltab) {
+            p.has_post = 2;
+            if (pre) p.has_pre = 2;
+            for (int z = 0; z < nz; z++) { p.post_full[z] = ft[z]->full.p; p.pre_row[z] = ft[z]->row.p; }
+        }
         p.tw = twA;
         launch_pass(l1, p, dim3((unsigned)(n2 / T), nc, nz), s, alg_bytes_per_col * nc);
         // pass B: scratch rows k1 (contiguous i2) -> out[k1 + n1*k2]
@@ -384,7 +463,7 @@ static void ntt_generic(NttTables& tabs, const u64* in, size_t in_cs, size_t in_
         q.out_c = out_cs; q.out_b = T; q.out_r = n1; q.out_t = 1; q.out_z = out_zs;
         q.T = T; q.t_is_column = 0; q.ncols_total = nc;
         q.load_t_fast = 0; q.store_t_fast = 1;
-        q.has_pre = 0; q.has_post = 0; q.scale = final_scale;
+        q.has_pre = 0; q.has_post = 0; q.scale = fulltab ? 1 : final_scale;
         q.tw = twB;
         launch_pass(l2, q, dim3((unsigned)(n1 / T), nc, nz), s, 0.0);
     }
@@ -407,10 +486,14 @@ void lde_coset(NttTables& t, const u64* coeffs, size_t in_cs, u64* lde, size_t o
     const size_t n = (size_t)1 << log_n;
     PowTable pre[8];
     std::shared_ptr<PowTableOwner> keep[8];
-    for (int z = 0; z < nz; z++) { keep[z] = get_shift(t, log_n, rate_bits, coset_begin + z, 0, s, shift_exp_bits); pre[z] = keep[z]->view; }
+    ShiftKey keys[8];
+    for (int z = 0; z < nz; z++) {
+        keep[z] = get_shift(t, log_n, rate_bits, coset_begin + z, 0, s, shift_exp_bits); pre[z] = keep[z]->view;
+        keys[z] = {rate_bits, coset_begin + z, shift_exp_bits};
+    }
     // section 8(d): the LDE writes 8*n bytes per coset and column; its input is the coefficient vector the preceding iNTT (or
     // fold) just wrote, which the survey's 48*n*C figure for iNTT + LDE does not count a second time
-    ntt_generic(t, coeffs, in_cs, 0, lde + (size_t)coset_begin * n, out_cs, n, ncols, nz, log_n, 0, pre, 1, s, 8.0 * nz * n);
+    ntt_generic(t, coeffs, in_cs, 0, lde + (size_t)coset_begin * n, out_cs, n, ncols, nz, log_n, 0, pre, 1, s, 8.0 * nz * n, keys);
 }
 
 // values on the coset 7*H_n (natural order) -> coefficients:  ifft then scale coefficient i by 7^-i.

@@ -1,4 +1,5 @@
 #include "batch.cuh"
+#include <cstdlib>
 #include "shard.cuh"
 #include <memory>
 #include <map>
@@ -108,6 +109,24 @@ Ctx& ctx() {
     if (t_ctx) return *t_ctx;
     if (!g_ctx) throw std::runtime_error("zkm_b200: not initialised (call zkm_b200_init; a CUDA device is required)");
     return *g_ctx;
+}
+bool blocking_sync_enabled() {
+    static const bool on = std::getenv("ZKM_BLOCKING_SYNC") && atoi(std::getenv("ZKM_BLOCKING_SYNC")) != 0;
+    return on;
+}
+cudaError_t stream_sync(cudaStream_t s) {
+    if (!blocking_sync_enabled()) return cudaStreamSynchronize(s);
+    static thread_local cudaEvent_t ev = nullptr;          // one per host thread, never destroyed (threads are few and long-lived)
+    static thread_local int ev_device = -1;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!ev || ev_device != dev) {
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return e;
+        ev_device = dev;
+    }
+    if ((e = cudaEventRecord(ev, s)) != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
 }
 Ctx::~Ctx() {
     for (int k = 0; k < BOUNCE_SLOTS; k++) {

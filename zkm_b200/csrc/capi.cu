@@ -56,7 +56,7 @@ int zkm_b200_shutdown(char** err) {
 uint64_t zkm_b200_launch_count(void) { return g_launch_count; }
 int zkm_b200_sync(char** err) {
     ZKM_API_BEGIN
-    ZKM_CUDA(cudaStreamSynchronize(ctx().stream));
+    ZKM_CUDA(stream_sync(ctx().stream));
     ZKM_API_END
 }
 
@@ -240,7 +240,7 @@ static cudaError_t upload_bounced(Ctx* c, void* dst, const void* src, size_t byt
         cudaError_t e;
         if (!c->bounce[k]) {
             if ((e = cudaHostAlloc(&c->bounce[k], Ctx::BOUNCE_BYTES, cudaHostAllocDefault)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&c->bounce_free[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&c->bounce_free[k], cudaEventDisableTiming | (blocking_sync_enabled() ? cudaEventBlockingSync : 0))) != cudaSuccess) return e;
         } else if ((e = cudaEventSynchronize(c->bounce_free[k])) != cudaSuccess) return e;      // the slot's last DMA has finished
         const char* from = (const char*)src + off;
         char* slot = (char*)c->bounce[k];
@@ -393,7 +393,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                                                             ar::RC_FREQUENCIES, d_bad, cs);
                                 unsigned bad = 0;
                                 e = cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, cs);
-                                if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+                                if (e == cudaSuccess) e = stream_sync(cs);
                                 if (e == cudaSuccess && bad) {
                                     std::lock_guard<std::mutex> lk(up.mu);
                                     if (up.error.empty()) up.error = "column value exceeds the max range value 65536";
@@ -411,7 +411,7 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                     std::vector<u64> pack((size_t)tables[t].ncols * n);
                     for (uint32_t i = 0; i < tables[t].ncols; i++) memcpy(pack.data() + (size_t)i * n, tables[t].cols[i], n * sizeof(u64));
                     e = cudaMemcpyAsync(dst[t], pack.data(), pack.size() * sizeof(u64), cudaMemcpyHostToDevice, cs);
-                    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);      // `pack` is released at the end of this scope
+                    if (e == cudaSuccess) e = stream_sync(cs);      // `pack` is released at the end of this scope
                 } else
                 for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++) {
                     e = upload_bounced(cptr, dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cs);
@@ -728,7 +728,7 @@ int zkm_b200_synth_columns_device(uint64_t* d_out, uint32_t ncols, uint32_t log_
     dim3 grid((unsigned)((n + 255) / 256), ncols);
     synth_columns_kernel<<<grid, 256, 0, c.stream>>>(d_out, n, seed);
     ZKM_LAUNCHED();
-    ZKM_CUDA(cudaStreamSynchronize(c.stream));
+    ZKM_CUDA(stream_sync(c.stream));
     ZKM_API_END
 }
 
@@ -782,9 +782,9 @@ static void synth_trace_dev(int system_id, uint32_t table, uint32_t log_n, uint6
         ZKM_CUDA(cudaMemcpyAsync(df.p, flags.data(), flags.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
         synth_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_out, n, (const int*)df.p, (int)flags.size(), seed);
         ZKM_LAUNCHED();
-        ZKM_CUDA(cudaStreamSynchronize(c.stream));
+        ZKM_CUDA(stream_sync(c.stream));
     }
-    ZKM_CUDA(cudaStreamSynchronize(c.stream));
+    ZKM_CUDA(stream_sync(c.stream));
 }
 
 int zkm_b200_synth_trace_device(int system_id, uint32_t table, uint32_t log_n, uint64_t seed, uint64_t* d_out, char** err) {

@@ -98,7 +98,7 @@ void DProgram::upload(cudaStream_t s) {
     b.resize((b.size() + 15) & ~(size_t)15);
     blob.alloc(b.size() / 8 + 2, s);
     ZKM_CUDA(cudaMemcpyAsync(blob.p, b.data(), b.size(), cudaMemcpyHostToDevice, s));
-    ZKM_CUDA(cudaStreamSynchronize(s));
+    ZKM_CUDA(stream_sync(s));
     unsigned char* base = (unsigned char*)blob.p;
     view.cols = (const DColumn*)(base + o_cols); view.terms = (const DTerm*)(base + o_terms);
     view.filters = (const DFilter*)(base + o_filters); view.pairs = (const int*)(base + o_pairs);

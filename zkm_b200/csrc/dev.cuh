@@ -37,6 +37,13 @@ void arena_free(void* p, size_t bytes);
 void arena_trim();                 // cudaFree every cached block
 size_t arena_cached_bytes();
 
+// Host wait for a stream: cudaStreamSynchronize (the driver spins), or -- ZKM_BLOCKING_SYNC=1 -- a wait on an event created with
+// cudaEventBlockingSync, which frees the waiting thread's core.  Measured (profiles/r2q_blocking_sync_ab.txt, 24 host threads
+// for 2 GPUs x 3 proofs in flight): spinning is 2.6 % faster on one GPU and 11 % faster end to end on two, so spinning is the
+// default; the blocking wait is for hosts with fewer cores than waiting threads.
+cudaError_t stream_sync(cudaStream_t s);
+bool blocking_sync_enabled();
+
 struct DevBuf {
     u64* p = nullptr;
     size_t n = 0;            // elements (u64)
@@ -65,7 +72,7 @@ struct DevBuf {
     }
     void download(u64* h, size_t cnt, size_t off = 0) const {
         ZKM_CUDA(cudaMemcpyAsync(h, p + off, cnt * sizeof(u64), cudaMemcpyDeviceToHost, stream));
-        ZKM_CUDA(cudaStreamSynchronize(stream));
+        ZKM_CUDA(stream_sync(stream));
     }
 };
 

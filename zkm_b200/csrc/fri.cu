@@ -193,7 +193,7 @@ void fri_reduce_batches(const Batch& trace, const Batch& aux, const Batch& quot,
     if (n < 4096) fri_reduce_small_kernel<<<(unsigned)n, 256, 0, s>>>(p);
     else fri_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
     ZKM_LAUNCHED();
-    ZKM_CUDA(cudaStreamSynchronize(s));           // h / ap lifetime
+    ZKM_CUDA(stream_sync(s));           // h / ap lifetime
 }
 
 void fri_combine(const u64* d_r, int log_n, gl2 zeta, gl2 zeta_next, gl2 v0, gl2 v1, gl2 v2, gl2 a0, gl2 a1, u64* d_out, cudaStream_t s) {

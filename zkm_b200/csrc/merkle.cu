@@ -189,7 +189,7 @@ void merkle_build_from_leaf_digests(MerkleTreeDev& t, cudaStream_t s) {
     t.cap.resize(ncap);
     if (!sharded) {
         ZKM_CUDA(cudaMemcpyAsync(t.cap.data(), t.digests.p + t.level_off.back(), ncap * sizeof(u64), cudaMemcpyDeviceToHost, s));
-        ZKM_CUDA(cudaStreamSynchronize(s));
+        ZKM_CUDA(stream_sync(s));
         return;
     }
     // the only exchange of a sharded commitment: every rank contributes the cap entries of its leaf quarters (ncclAllGather,

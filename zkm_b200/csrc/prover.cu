@@ -452,7 +452,7 @@ void stage_single_table(int system_id, int table_index, const StarkCfg& cfg, Dev
     for (int i = zstart; i < naux; i++) open_out.push_back(h[(i * 3 + 2) * 2]);
     eval_polys_at_points(quot.coeffs.p, Q, log_n, pts, 1, h.data(), s);
     for (int i = 0; i < Q; i++) { open_out.push_back(h[i * 2]); open_out.push_back(h[i * 2 + 1]); }
-    ZKM_CUDA(cudaStreamSynchronize(s));
+    ZKM_CUDA(stream_sync(s));
 }
 
 std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<TableInput>& inputs, const PublicInputs& pv) {
@@ -527,7 +527,7 @@ std::vector<u64> prove_system(int system_id, const StarkCfg& cfg, std::vector<Ta
             j.trace = Batch();                                  // release this table's device memory
         }
     }
-    ZKM_CUDA(cudaStreamSynchronize(s));
+    ZKM_CUDA(stream_sync(s));
     return std::move(W.w);
 }
 

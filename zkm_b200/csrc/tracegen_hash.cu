@@ -351,7 +351,7 @@ size_t sponge_log_table(Kernel kernel, const char* family, const char* what, siz
     if (n_ops) {
         kernel<<<(unsigned)((n_ops + 63) / 64), 64, 0, s>>>(log.p, index.p, n_ops, n, cols.p);
         ZKM_LAUNCHED();
-        ZKM_CUDA(cudaStreamSynchronize(s));        // si.idx is host memory of this frame
+        ZKM_CUDA(stream_sync(s));        // si.idx is host memory of this frame
     }
     return n;
 }

@@ -412,7 +412,15 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                     for (uint32_t i = 0; i < tables[t].ncols; i++) memcpy(pack.data() + (size_t)i * n, tables[t].cols[i], n * sizeof(u64));
                     e = cudaMemcpyAsync(dst[t], pack.data(), pack.size() * sizeof(u64), cudaMemcpyHostToDevice, cs);
                     if (e == cudaSuccess) e = stream_sync(cs);      // `pack` is released at the end of this scope
-                } else
+                } else {
+                // Large tables of concurrent proofs (worker contexts) take turns on the PCIe link instead of splitting it: a
+                // proof whose upload owns the link has its data after 1/k of the time k interleaved uploads would need and
+                // starts computing while the next proof uploads (ZKM_UPLOAD_FIFO=0: A/B switch).
+                static std::mutex link_mu;
+                static const bool fifo = !(std::getenv("ZKM_UPLOAD_FIFO") && atoi(std::getenv("ZKM_UPLOAD_FIFO")) == 0);
+                std::unique_lock<std::mutex> link(link_mu, std::defer_lock);
+                // (pageable sources are bound by the host-side copy into the bounce ring, not by the link: they stay concurrent)
+                if (fifo && (size_t)tables[t].ncols * n * sizeof(u64) >= ((size_t)64 << 20) && !source_is_pageable(tables[t].cols[0])) link.lock();
                 for (uint32_t i = 0; i < tables[t].ncols && e == cudaSuccess; i++) {
                     e = upload_bounced(cptr, dst[t] + (size_t)i * n, tables[t].cols[i], n * sizeof(u64), cs);
                     if (e == cudaSuccess && g < gends[t].size() && (int)i + 1 == gends[t][g]) {
@@ -422,6 +430,8 @@ static int prove_common(int system_id, const zkm_table_t* tables_in, uint32_t nu
                         up.groups_done[t] = (int)g;
                         up.cv.notify_all();
                     }
+                }
+                if (link.owns_lock() && e == cudaSuccess) e = stream_sync(cs);       // the link is free once this table has landed
                 }
                 if (e == cudaSuccess) e = cudaEventRecord(evs[t], cs);
                 std::lock_guard<std::mutex> lk2(up.mu);

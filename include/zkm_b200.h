@@ -279,7 +279,7 @@ int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t
  * views that are NOT #[repr(C)] (cpu/columns/general.rs:8-18,143-201), so their field order is formally up to rustc.  The Rust
  * shim therefore reports where its compiler actually put every field this library reads -- (key, value) pairs taken from
  * `COL_MAP` (mod.rs:184-189) and from `NUM_*_COLUMNS` -- and zkm_b200_layout_check compares them with the constants the
- * kernels were compiled with (zkm_b200/csrc/tables/*.h).  A mismatch is an error naming the key, before any proof is made.
+ * kernels were compiled with (the headers under zkm_b200/csrc/tables).  A mismatch is an error naming the key, before any proof is made.
  * Keys: ZKM_LK_NUM_COLUMNS + t = number of trace columns of table t (Table enum order, all_stark.rs:97-110); the CPU keys
  * below are absolute column indices, except the *_REL keys, which are relative to ZKM_LK_CPU_GENERAL resp. to the start of
  * one memory channel. */

@@ -114,13 +114,17 @@ struct Reader {
     const uint64_t* words(size_t k) { if (k > n - pos) throw Error("proof buffer truncated"); const uint64_t* r = p + pos; pos += k; return r; }
     std::vector<F> fs() { size_t k = (size_t)u(); const uint64_t* w = words(k); return std::vector<F>(w, w + k); }
     std::vector<Ext> exts() {
-        size_t k = (size_t)u(); const uint64_t* w = words(2 * k);
+        size_t k = (size_t)u();
+        if (k > (n - pos) / 2) throw Error("proof buffer truncated");
+        const uint64_t* w = words(2 * k);
         std::vector<Ext> v(k);
         for (size_t i = 0; i < k; i++) { v[i].a = w[2 * i]; v[i].b = w[2 * i + 1]; }
         return v;
     }
     std::vector<HashOut> hashes() {
-        size_t k = (size_t)u(); const uint64_t* w = words(4 * k);
+        size_t k = (size_t)u();
+        if (k > (n - pos) / 4) throw Error("proof buffer truncated");
+        const uint64_t* w = words(4 * k);
         std::vector<HashOut> v(k);
         for (size_t i = 0; i < k; i++) for (int j = 0; j < 4; j++) v[i].elements[j] = w[4 * i + j];
         return v;

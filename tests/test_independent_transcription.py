@@ -217,7 +217,196 @@ def sha_compress_sponge_constraints(lv, nv, yc):
             yc.constraint(c * real)
 
 
-TABLES = {"Memory": (11, 13, memory_constraints), "Logic": (10, 69, logic_constraints),
+SHA_K = [
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2]      # FIPS 180-4
+
+
+def sha_compress_constraints(lv, nv, yc):
+    """sha_compress/sha_compress_stark.rs:399-606; view sha_compress/columns.rs:9-55; gadgets not_operation.rs:23-33,
+    wrapping_add_5.rs:37-82, wrapping_add_2.rs, sha_extend/rotate_right.rs, sha_compress/logic.rs:7-16; round constants
+    sha_compress_sponge/constants.rs (their little-endian bytes)."""
+    STATE, E_NOT, W_I, K_I, S_1, CH, S_0, MAJ = 0, 32, 36, 40, 48, 60, 68, 88
+    E_RR_6, E_RR_11, E_RR_25, A_RR_2, A_RR_13, A_RR_22 = 92, 98, 104, 110, 116, 122
+    TEMP2, D_ADD_TEMP1, TEMP1_ADD_TEMP2, TIMESTAMP, W_I_VIRT, TEMP1, ROUND = 128, 134, 140, 146, 149, 150, 159
+    st = lambda i: STATE + 4 * i
+    is_final = lv[ROUND + 64]
+    yc.constraint(is_final * (is_final - 1))
+    not_final = 1 - is_final
+    flags = sum(lv[ROUND + i] for i in range(65))
+    yc.constraint(flags * (flags - 1))
+    for i in range(4):
+        byte_i = sum(lv[ROUND + j] * ((SHA_K[j] >> (8 * i)) & 0xFF) for j in range(64))
+        yc.constraint(flags * not_final * (lv[K_I + i] - byte_i))
+    for op, inp, r in ((E_RR_6, st(4), 6), (E_RR_11, st(4), 11), (E_RR_25, st(4), 25), (A_RR_2, st(0), 2), (A_RR_13, st(0), 13), (A_RR_22, st(0), 22)):
+        for c in _rotate_right(lv, inp, op, r):
+            yc.constraint(c)
+    for i in range(4):
+        yc.constraint(flags * (lv[st(4) + i] + lv[E_NOT + i] - 255))
+    for c in _wrapping_add(lv, (st(7), S_1, CH, K_I, W_I), TEMP1, 5):
+        yc.constraint(flags * c)
+    for inputs, op in (((S_0, MAJ), TEMP2), ((st(3), TEMP1), D_ADD_TEMP1), ((TEMP1, TEMP2), TEMP1_ADD_TEMP2)):
+        for c in _wrapping_add(lv, inputs, op, 2):
+            yc.constraint(flags * c)
+    yc.constraint(flags * not_final * (nv[TIMESTAMP] - lv[TIMESTAMP]))
+    yc.constraint(flags * not_final * (nv[W_I_VIRT] - lv[W_I_VIRT] - 4))
+    for cur, nxt in ((TEMP1_ADD_TEMP2, st(0)), (st(0), st(1)), (st(1), st(2)), (st(2), st(3)), (D_ADD_TEMP1, st(4)), (st(4), st(5)), (st(5), st(6)),
+                     (st(6), st(7))):
+        for i in range(4):
+            yc.constraint(flags * not_final * (lv[cur + i] - nv[nxt + i]))
+
+
+# ---------------------------------------------------------------------------------------------------------- Poseidon
+def _poseidon_constants():
+    """The reference's poseidon/constants.rs tables as extracted into oracle/poseidon_consts.h by tools/gen_poseidon_consts.py
+    (data, pinned by the permutation's known answers -- not part of the constraint transcription being cross-checked)."""
+    import re
+    text = (ROOT / "oracle/poseidon_consts.h").read_text().replace("\\\n", " ")
+    out = {}
+    for name, body in re.findall(r"#define POSEIDON_(\w+)_INIT \{([^}]*)\}", text):
+        out[name] = [int(x.rstrip("ULL"), 0) for x in re.findall(r"0x[0-9a-fA-F]+(?:ULL)?|\b\d+(?:ULL)?", body)]
+    return out
+
+
+def poseidon_constraints(lv, nv, yc):
+    """poseidon/poseidon_stark.rs:554-594 with the layer helpers :165-170 (constants), :184-192,245-267 (S-box witness),
+    :294-308 (MDS), :371-375,402-414 (first partial-round constants, initial matrix), :436-448,503-519 (partial rounds);
+    columns poseidon/columns.rs:3-60."""
+    K = _poseidon_constants()
+    RC, CIRC, DIAG = K["ALL_ROUND_CONSTANTS"], K["MDS_CIRC"], K["MDS_DIAG"]
+    FIRST, PRC, VS, WH, INIT = (K["FAST_PARTIAL_FIRST_ROUND_CONSTANT"], K["FAST_PARTIAL_ROUND_CONSTANTS"], K["FAST_PARTIAL_ROUND_VS"],
+                                K["FAST_PARTIAL_ROUND_W_HATS"], K["FAST_PARTIAL_ROUND_INITIAL_MATRIX"])
+    assert (len(RC), len(VS), len(WH), len(INIT)) == (360, 242, 242, 121)
+    W, HALF, NP = 12, 4, 22
+    reg_in = lambda i: 1 + i
+    reg_out = lambda i: 1 + W + i
+    start_full0 = 1 + 2 * W + 1
+    start_partial = start_full0 + 2 * W * HALF
+    start_full1 = start_partial + 2 * NP
+    state = [lv[reg_in(i)] for i in range(W)]
+
+    def sbox(x, inter, out):
+        yc.constraint((x * x * x - inter) % P)
+        yc.constraint((x * inter * inter - out) % P)
+
+    def full(r, first, ctr):
+        nonlocal state
+        state = [(state[i] + RC[i + W * ctr]) % P for i in range(W)]
+        base = start_full0 if first else start_full1
+        for i in range(W):
+            inter, out = lv[base + 2 * W * r + 2 * i], lv[base + 2 * W * r + 2 * i + 1]
+            sbox(state[i], inter, out)
+            state[i] = out
+        state = [(sum(state[(j + i) % W] * CIRC[j] for j in range(W)) + state[i] * DIAG[i]) % P for i in range(W)]
+    ctr = 0
+    for r in range(HALF):
+        full(r, True, ctr)
+        ctr += 1
+    state = [(state[i] + FIRST[i]) % P for i in range(W)]
+    res = [state[0]] + [0] * (W - 1)
+    for r in range(1, W):
+        for c in range(1, W):
+            res[c] = (res[c] + state[r] * INIT[(r - 1) * 11 + (c - 1)]) % P
+    state = res
+
+    def partial_mds(r):
+        nonlocal state
+        d = state[0] * (CIRC[0] + DIAG[0])
+        for i in range(1, W):
+            d += state[i] * WH[r * 11 + i - 1]
+        state = [d % P] + [(state[0] * VS[r * 11 + i - 1] + state[i]) % P for i in range(1, W)]
+    for r in range(NP):
+        inter, out = lv[start_partial + 2 * r], lv[start_partial + 2 * r + 1]
+        sbox(state[0], inter, out)
+        state[0] = out
+        if r < NP - 1:
+            state[0] = (state[0] + PRC[r]) % P
+        partial_mds(r)
+    ctr += NP
+    for r in range(HALF):
+        full(r, False, ctr)
+        ctr += 1
+    for i in range(W):
+        yc.constraint(state[i] - lv[reg_out(i)])
+
+
+# ------------------------------------------------------------------------------------------------------------ Keccak
+KECCAK_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B, 0x0000000080000001,
+             0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088, 0x0000000080008009, 0x000000008000000A,
+             0x000000008000808B, 0x800000000000008B, 0x8000000000008089, 0x8000000000008003, 0x8000000000008002, 0x8000000000000080,
+             0x000000000000800A, 0x800000008000000A, 0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]   # FIPS 202
+KECCAK_ROT = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]                      # keccak/columns.rs:41-47
+
+
+def keccak_constraints(lv, nv, yc):
+    """keccak/keccak_stark.rs:248-415; columns keccak/columns.rs:8-131; xor_gen / xor3_gen / andn_gen keccak/logic.rs:16-23,54-56;
+    round-constant bits keccak/constants.rs (bit i of RC[round], least significant first)."""
+    ROUNDS, TIMESTAMP = 24, 24
+    START_A = 25
+    START_C = START_A + 50
+    START_CP = START_C + 320
+    START_AP = START_CP + 320
+    START_APP = START_AP + 1600
+    START_APP00 = START_APP + 50
+    APPP00_LO = START_APP00 + 64
+    assert APPP00_LO + 2 == len(lv) == 2431
+    reg_a = lambda x, y: START_A + (x * 5 + y) * 2
+    reg_c = lambda x, z: START_C + x * 64 + z
+    reg_cp = lambda x, z: START_CP + x * 64 + z
+    reg_ap = lambda x, y, z: START_AP + x * 320 + y * 64 + z
+    reg_app = lambda x, y: START_APP + x * 10 + y * 2
+    reg_appp = lambda x, y: APPP00_LO if (x, y) == (0, 0) else reg_app(x, y)
+
+    def reg_b(x, y, z):
+        a, b = (x + 3 * y) % 5, x
+        return reg_ap(a, b, (z + 64 - KECCAK_ROT[a][b]) % 64)
+    xor = lambda x, y: (x + y - 2 * x * y) % P
+    xor3 = lambda x, y, z: xor(x, xor(y, z))
+    andn = lambda x, y: (1 - x) * y % P
+    limb = lambda bits: sum(b << k for k, b in enumerate(bits))
+    filt = lv[ROUNDS - 1]
+    yc.constraint(filt * (filt - 1))
+    not_final = 1 - lv[ROUNDS - 1]
+    yc.constraint(not_final * filt)
+    flags = sum(lv[i] for i in range(ROUNDS))
+    yc.constraint(flags * not_final * (nv[TIMESTAMP] - lv[TIMESTAMP]))
+    for x in range(5):
+        for z in range(64):
+            yc.constraint(lv[reg_cp(x, z)] - xor3(lv[reg_c(x, z)], lv[reg_c((x + 4) % 5, z)], lv[reg_c((x + 1) % 5, (z + 63) % 64)]))
+    for x in range(5):
+        for y in range(5):
+            bit = lambda z: xor3(lv[reg_ap(x, y, z)], lv[reg_c(x, z)], lv[reg_cp(x, z)])
+            yc.constraint(limb([bit(z) for z in range(32)]) - lv[reg_a(x, y)])
+            yc.constraint(limb([bit(z) for z in range(32, 64)]) - lv[reg_a(x, y) + 1])
+    for x in range(5):
+        for z in range(64):
+            diff = sum(lv[reg_ap(x, i, z)] for i in range(5)) - lv[reg_cp(x, z)]
+            yc.constraint(diff * (diff - 2) * (diff - 4))
+    for x in range(5):
+        for y in range(5):
+            bit = lambda z: xor(lv[reg_b(x, y, z)], andn(lv[reg_b((x + 1) % 5, y, z)], lv[reg_b((x + 2) % 5, y, z)]))
+            yc.constraint(limb([bit(z) for z in range(32)]) - lv[reg_app(x, y)])
+            yc.constraint(limb([bit(z) for z in range(32, 64)]) - lv[reg_app(x, y) + 1])
+    bits00 = [lv[START_APP00 + i] for i in range(64)]
+    yc.constraint(limb(bits00[:32]) - lv[reg_app(0, 0)])
+    yc.constraint(limb(bits00[32:]) - lv[reg_app(0, 0) + 1])
+    xored = lambda i: xor(bits00[i], sum(lv[r] * ((KECCAK_RC[r] >> i) & 1) for r in range(ROUNDS)))
+    yc.constraint(limb([xored(z) for z in range(32)]) - lv[APPP00_LO])
+    yc.constraint(limb([xored(z) for z in range(32, 64)]) - lv[APPP00_LO + 1])
+    not_last = 1 - lv[ROUNDS - 1]
+    for x in range(5):
+        for y in range(5):
+            yc.constraint_transition(not_last * (lv[reg_appp(x, y)] - nv[reg_a(x, y)]))
+            yc.constraint_transition(not_last * (lv[reg_appp(x, y) + 1] - nv[reg_a(x, y) + 1]))
+
+
+TABLES = {"Memory": (11, 13, memory_constraints), "Logic": (10, 69, logic_constraints), "ShaCompress": (8, 224, sha_compress_constraints),
+          "Keccak": (4, 2431, keccak_constraints),
+          "Poseidon": (2, 262, poseidon_constraints),
           "KeccakSponge": (5, 470, keccak_sponge_constraints), "PoseidonSponge": (3, 110, poseidon_sponge_constraints),
           "ShaExtend": (6, 78, sha_extend_constraints), "ShaExtendSponge": (7, 76, sha_extend_sponge_constraints),
           "ShaCompressSponge": (9, 127, sha_compress_sponge_constraints)}

@@ -404,7 +404,205 @@ def keccak_constraints(lv, nv, yc):
             yc.constraint_transition(not_last * (lv[reg_appp(x, y) + 1] - nv[reg_a(x, y) + 1]))
 
 
+# -------------------------------------------------------------------------------------------------------- Arithmetic
+def _sign_extend_poly():
+    """arithmetic/sra.rs:271-282: the interpolant through (0, 0), (i, 2^31 + .. + 2^(32-i)) for i = 1..31 (plonky2's
+    `interpolant` = the unique polynomial of degree < 32), coefficients low to high."""
+    pts, acc = [(0, 0)], 0
+    for i in range(1, 32):
+        acc += 1 << (32 - i)
+        pts.append((i, acc))
+    coeffs = [0] * 32
+    for k, (xk, yk) in enumerate(pts):
+        num, den = [1], 1                                   # prod_{j != k} (x - xj), low to high
+        for j, (xj, _) in enumerate(pts):
+            if j == k:
+                continue
+            num = [(a - xj * b) % P for a, b in zip([0] + num, num + [0])]
+            den = den * (xk - xj) % P
+        scale = yk * pow(den, P - 2, P) % P
+        for d in range(32):
+            coeffs[d] = (coeffs[d] + num[d] * scale) % P
+    return coeffs
+
+
+def arithmetic_constraints(lv, nv, yc):
+    """arithmetic/arithmetic_stark.rs:198-229 and the modules it calls, in its order: mul.rs:126-188, mult.rs:158-318,
+    addcy.rs:87-160, slt.rs:50-112, lui.rs:51-71, div.rs:361-628, shift.rs:93-134, sra.rs:93-155, lo_hi.rs:25-36; column map
+    arithmetic/columns.rs (N_LIMBS = 2), polynomial helpers arithmetic/utils.rs."""
+    (IS_ADD, IS_ADDU, IS_ADDI, IS_ADDIU, IS_SUB, IS_SUBU, IS_MULT, IS_MULTU, IS_MUL, IS_DIV, IS_DIVU, IS_SLLV, IS_SRLV, IS_SRAV, IS_SLL, IS_SRL,
+     IS_SRA, IS_SLT, IS_SLTU, IS_SLTI, IS_SLTIU, IS_LUI, IS_MFHI, IS_MTHI, IS_MFLO, IS_MTLO) = range(26)
+    S = 26
+    IN0, IN1, IN2, OUT, AUXIN0, AUXIN1, AUXIN2 = (range(S + 2 * k, S + 2 * k + 2) for k in range(7))
+    AUX_REG_0, AUX_REG_1, AUX_REG_2 = range(S, S + 2), range(S + 2, S + 6), range(S + 6, S + 9)
+    MOD_OUT_AUX_RED, MOD_IS_ZERO, MOD_AUX_LO, MOD_AUX_HI, DENOM_IS_ZERO = AUX_REG_0, AUX_REG_1[0], range(AUX_REG_1[0] + 1, AUX_REG_1[-1] + 1), AUX_REG_2, AUX_REG_2[-1] + 1
+    RANGE_COUNTER = S + 18
+    RC_FREQ = RANGE_COUNTER + 1
+    AUX_EXTRA = range(RC_FREQ + 1, RC_FREQ + 9)
+    OUT_LO, OUT_HI = OUT, range(OUT[-1] + 1, OUT[-1] + 3)
+    MULT_AUX_LO = range(OUT_HI[-1] + 1, OUT_HI[-1] + 5)
+    MULT_AUX_HI = range(MULT_AUX_LO[-1] + 1, MULT_AUX_LO[-1] + 5)
+    QUOT_ABS = range(AUXIN2[-1] + 1, AUXIN2[-1] + 3)
+    REM_ABS = range(QUOT_ABS[-1] + 1, QUOT_ABS[-1] + 3)
+    assert len(lv) == S + 18 + 10 == 54
+    BASE, OFFSET, INV = 1 << 16, 1 << 20, 18446462594437939201
+    assert BASE * INV % P == 1
+    rd = lambda v, rng: [v[i] for i in rng]
+
+    def mul_lo(a, b):
+        return [sum(a[i] * b[d - i] for i in range(d + 1)) for d in range(len(a))]
+
+    def adjoin_root(a, root):
+        return [-root * a[0]] + [a[d - 1] - root * a[d] for d in range(1, len(a))]
+
+    def mul_like(filt, left, right, out, aux_lo, aux_hi):          # mul.rs:126-177 / mult.rs:275-318
+        aux = [lv[lo] + lv[hi] * BASE - OFFSET for lo, hi in zip(aux_lo, aux_hi)]
+        poly = [c - o - r for c, o, r in zip(mul_lo(left, right), out, adjoin_root(aux, BASE))]
+        for c in poly:
+            yc.constraint(filt * c)
+
+    def addcy(filt, x, y, z, given_cy, two_row):                   # addcy.rs:87-140
+        emit = yc.constraint_transition if two_row else yc.constraint
+        cy = 0
+        for xi, yi, zi in zip(x, y, z):
+            t = cy + xi + yi - zi
+            emit(filt * t * (BASE - t))
+            cy = t * INV
+        if not two_row:
+            emit(filt * given_cy[0] * (given_cy[0] - 1))
+        emit(filt * (cy - given_cy[0]))
+        for i in range(1, 2):
+            emit(filt * given_cy[i])
+
+    div_like_flags = lv[IS_DIV] + lv[IS_DIVU] + lv[IS_SRL] + lv[IS_SRLV] + lv[IS_SRA] + lv[IS_SRAV]
+
+    def div_helper(filt, num_rng, den_rng, quo_rng, rem_rng):      # div.rs:605-633 with modular_constr_poly :395-469, check_reduced :361-393
+        yc.constraint_last_row(filt)
+        num, modulus, quo, output = rd(lv, num_rng), rd(lv, den_rng), rd(lv, quo_rng) + [0, 0], rd(lv, rem_rng)
+        mod_is_zero = nv[MOD_IS_ZERO]
+        yc.constraint_transition(filt * (mod_is_zero * mod_is_zero - mod_is_zero))
+        yc.constraint_transition(filt * sum(modulus) * mod_is_zero)
+        modulus[0] += mod_is_zero
+        denom_is_zero = nv[DENOM_IS_ZERO]
+        yc.constraint_transition(filt * (mod_is_zero * div_like_flags - denom_is_zero))
+        output[0] += denom_is_zero
+        addcy(filt, modulus, rd(nv, MOD_OUT_AUX_RED), output, [1 - mod_is_zero * div_like_flags, 0], True)
+        output[0] -= denom_is_zero
+        prod = [0] * 5
+        for i, qi in enumerate(quo):
+            for j, mj in enumerate(modulus):
+                prod[i + j] += qi * mj
+        for x in prod[4:]:
+            yc.constraint_transition(filt * x)
+        poly = prod[:4]
+        for i, o in enumerate(output):
+            poly[i] += o
+        aux = [nv[i] - OFFSET for i in MOD_AUX_LO] + [0]
+        for k, j in enumerate(MOD_AUX_HI):
+            aux[k] += BASE * nv[j]
+        poly = [c + r for c, r in zip(poly, adjoin_root(aux, BASE))]
+        for i, x in enumerate(num):
+            poly[i] -= x
+        for c in poly:
+            yc.constraint_transition(filt * c)
+
+    # range counter (arithmetic_stark.rs:209-217)
+    rc1, rc2 = lv[RANGE_COUNTER], nv[RANGE_COUNTER]
+    yc.constraint_first_row(rc1)
+    yc.constraint_transition((rc2 - rc1) * (rc2 - rc1) - (rc2 - rc1))
+    yc.constraint_last_row(rc1 - ((1 << 16) - 1))
+    # mul
+    mul_like(lv[IS_MUL], rd(lv, IN0), rd(lv, IN1), rd(lv, OUT), AUXIN0, AUXIN1)
+    # mult / multu
+    out4 = rd(lv, OUT_LO) + rd(lv, OUT_HI)
+    filt = lv[IS_MULT]
+
+    def sign_extend(is_neg_idx, sum_idx, inp):
+        is_neg = lv[is_neg_idx]
+        yc.constraint(filt * is_neg * (1 - is_neg))
+        yc.constraint(filt * (inp[1] + (1 << 15) - lv[sum_idx] - is_neg * BASE))
+        return inp + [is_neg * 0xFFFF] * 2
+    left = sign_extend(AUX_EXTRA[0], IN2[0], rd(lv, IN0))
+    right = sign_extend(AUX_EXTRA[0] + 1, IN2[0] + 1, rd(lv, IN1))
+    mul_like(filt, left, right, out4, MULT_AUX_LO, MULT_AUX_HI)
+    mul_like(lv[IS_MULTU], rd(lv, IN0) + [0, 0], rd(lv, IN1) + [0, 0], out4, MULT_AUX_LO, MULT_AUX_HI)
+    # addcy
+    in0, in1, out, aux = rd(lv, IN0), rd(lv, IN1), rd(lv, OUT), rd(lv, AUXIN0)
+    addcy(lv[IS_ADD], in0, in1, out, aux, False)
+    addcy(lv[IS_SUB], in1, out, in0, aux, False)
+    addcy(lv[IS_ADDI], in0, in1, out, aux, False)
+    addcy(lv[IS_ADDIU], in0, in1, out, aux, False)
+    # slt (slt.rs:50-112: x = in1, y = aux, z = in0, given_cy = AUX_INPUT_REGISTER_1, rd = out)
+    filt = lv[IS_SLT] + lv[IS_SLTU] + lv[IS_SLTI] + lv[IS_SLTIU]
+    sign = lv[IS_SLT] + lv[IS_SLTI]
+    given_cy, rdv = rd(lv, AUXIN1), out
+    cy = 0
+    for xi, yi, zi in zip(in1, aux, in0):
+        t = cy + xi + yi - zi
+        yc.constraint(filt * t * (BASE - t))
+        cy = t * INV
+    yc.constraint(filt * given_cy[0] * (given_cy[0] - 1))
+    yc.constraint(filt * (cy - given_cy[0]) * (1 - sign))
+    yc.constraint(filt * given_cy[1] * (1 - cy - given_cy[0]))
+    yc.constraint_transition(filt * (rdv[0] - given_cy[0]))
+    yc.constraint(filt * given_cy[1] * (1 - sign))
+    yc.constraint_transition(filt * rdv[1])
+    # lui
+    mul_like(lv[IS_LUI], rd(lv, IN0), rd(lv, IN1), rd(lv, OUT), AUXIN0, AUXIN1)
+    # divu, div (div.rs:481-603)
+    div_helper(lv[IS_DIVU], IN0, IN1, OUT, AUXIN0)
+    filt = lv[IS_DIV]
+
+    def check_abs(inp, abs_rng, sum_idx, is_neg_idx, borrow_idx):
+        is_neg = nv[is_neg_idx]
+        yc.constraint_transition(filt * is_neg * (1 - is_neg))
+        yc.constraint_transition(filt * (lv[inp[-1]] + (1 << 15) - nv[sum_idx] - is_neg * BASE))
+        borrow = nv[borrow_idx]
+        yc.constraint_transition(filt * borrow * (1 - borrow))
+        neg_inputs = [borrow * BASE - lv[inp[0]], BASE - lv[inp[0] + 1] - borrow]
+        for i, j, neg in zip(inp, abs_rng, neg_inputs):
+            yc.constraint_transition(filt * (is_neg * neg + (1 - is_neg) * lv[i] - lv[j]))
+        return is_neg
+    D = DENOM_IS_ZERO
+    n0 = check_abs(IN0, IN2, D + 1, D + 5, D + 6)
+    n1 = check_abs(IN1, AUXIN2, D + 2, D + 7, D + 8)
+    nq = check_abs(OUT_LO, QUOT_ABS, D + 3, RC_FREQ + 1, RC_FREQ + 2)
+    nr = check_abs(OUT_HI, REM_ABS, D + 4, RC_FREQ + 3, RC_FREQ + 4)
+    same = nv[RC_FREQ + 5]
+    yc.constraint_transition(filt * (n0 + n1 - 2 * n0 * n1 - same))
+    yc.constraint_transition(filt * (nq - same) * sum(rd(lv, OUT_LO)))
+    yc.constraint_transition(filt * (nr - n0) * sum(rd(lv, OUT_HI)))
+    div_helper(filt, IN2, AUXIN2, QUOT_ABS, REM_ABS)
+    # shift: sll as a multiplication, srl as a division (shift.rs:93-134)
+    mul_like(lv[IS_SLL] + lv[IS_SLLV], rd(lv, IN1), rd(lv, IN2), rd(lv, OUT), AUXIN0, AUXIN1)
+    div_helper(lv[IS_SRL] + lv[IS_SRLV], IN1, IN2, OUT, AUXIN0)
+    # sra (sra.rs:93-155)
+    filt = lv[IS_SRA] + lv[IS_SRAV]
+    shift = rd(lv, IN0)
+    yc.constraint_transition(filt * shift[1])
+    is_neg = lv[AUXIN2[-1] + 2]
+    yc.constraint_transition(filt * is_neg * (1 - is_neg))
+    yc.constraint_transition(filt * (lv[IN1[-1]] + (1 << 15) - lv[AUXIN2[-1] + 1] - is_neg * BASE))
+    shift_sq = nv[AUXIN2[-1] + 1]
+    yc.constraint_transition(filt * (shift_sq - shift[0] * shift[0]))
+    coeffs = _sign_extend_poly()[::-1]
+    acc = 0
+    for w, k in zip(rd(lv, AUX_EXTRA) + rd(nv, AUX_EXTRA), range(0, 32, 2)):
+        yc.constraint_transition(filt * (acc * shift_sq + coeffs[k] * shift[0] + coeffs[k + 1] - w))
+        acc = w
+    acc_lo, acc_hi = nv[AUXIN2[0]], nv[AUXIN2[0] + 1]
+    yc.constraint_transition(filt * (acc_hi * BASE + acc_lo - acc))
+    div_helper(filt, IN1, IN2, AUXIN2, AUXIN0)
+    for x, y, z in zip(rd(lv, AUXIN2), (acc_lo, acc_hi), rd(lv, OUT)):
+        yc.constraint_transition(filt * (x + y * is_neg - z))
+    # lo_hi
+    filt = lv[IS_MFHI] + lv[IS_MTHI] + lv[IS_MFLO] + lv[IS_MTLO]
+    for i, o in zip(rd(lv, IN0), rd(lv, OUT)):
+        yc.constraint(filt * (i - o))
+
+
 TABLES = {"Memory": (11, 13, memory_constraints), "Logic": (10, 69, logic_constraints), "ShaCompress": (8, 224, sha_compress_constraints),
+          "Arithmetic": (0, 54, arithmetic_constraints),
           "Keccak": (4, 2431, keccak_constraints),
           "Poseidon": (2, 262, poseidon_constraints),
           "KeccakSponge": (5, 470, keccak_sponge_constraints), "PoseidonSponge": (3, 110, poseidon_sponge_constraints),

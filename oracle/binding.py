@@ -59,6 +59,8 @@ def load():
     lib.orc_num_ctls.argtypes = [C.c_int]
     lib.orc_lookup_fingerprint.argtypes = [C.c_int, C.c_int, u64, u64p]
     lib.orc_gen_poseidon_rows.argtypes = [u64p, u64p, C.c_size_t, u64p]
+    lib.orc_table_constraint_values.restype = C.c_long
+    lib.orc_table_constraint_values.argtypes = [C.c_int, u64, u64p, C.c_size_t]
     lib.orc_stage_table.restype = C.c_long
     lib.orc_stage_table.argtypes = [C.c_int, C.c_uint32, C.POINTER(u64p), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), u64p, u64p, u64p, u64p,
                                     C.POINTER(C.c_uint32), u64p, u64p]

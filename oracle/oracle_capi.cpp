@@ -321,6 +321,27 @@ int orc_table_fingerprint(int kind, uint64_t seed, uint64_t out[3]) {
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+// The individual constraint values behind orc_table_fingerprint, in emission order (after the z_last / lagrange factors):
+// writes up to max_out values, returns their total number (or -1).  tests/test_independent_transcription.py compares them one
+// by one with a second, Python transcription of the reference.
+struct ListingConsumer : CountingConsumer {
+    std::vector<uint64_t> values;
+    void constraint(Fp c) { values.push_back(c.v); CountingConsumer::constraint(c); }
+    void constraint_transition(Fp c) { constraint(c * z_last); }
+    void constraint_first_row(Fp c) { constraint(c * l_first); }
+    void constraint_last_row(Fp c) { constraint(c * l_last); }
+};
+long orc_table_constraint_values(int kind, uint64_t seed, uint64_t* out, size_t max_out) {
+    try {
+        std::vector<Fp> lv, nv;
+        fp_rows(seed, zkm::tables::table_num_columns(kind), lv, nv);
+        ListingConsumer yc;
+        RowView<Fp> l{lv.data()}, nx{nv.data()};
+        if (!zkm::tables::eval_table<Fp, RowView<Fp>, ListingConsumer>(kind, l, nx, yc)) throw std::runtime_error("no constraints for this table");
+        for (size_t i = 0; i < yc.values.size() && i < max_out; i++) out[i] = yc.values[i];
+        return (long)yc.values.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
 // fold of (filter value, column values...) of one TableWithColumns on the frame above: acc <- acc * FP_ALPHA0 + v
 static Fp fp_table_with_columns(const zkm::tables::TableWithColumns& t, const Fp* lv, const Fp* nv) {
     Fp acc = filter_eval<Fp>(t.filter, lv, nv);

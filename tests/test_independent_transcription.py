@@ -601,13 +601,50 @@ def arithmetic_constraints(lv, nv, yc):
         yc.constraint(filt * (i - o))
 
 
+def cpu_table_constraints(lv, nv, yc):
+    """cpu/cpu_stark.rs:259-284 and the ten modules it calls: tests/cpu_constraints_ref.py."""
+    import cpu_constraints_ref
+    cpu_constraints_ref.cpu_constraints(lv, nv, yc)
+
+
 TABLES = {"Memory": (11, 13, memory_constraints), "Logic": (10, 69, logic_constraints), "ShaCompress": (8, 224, sha_compress_constraints),
-          "Arithmetic": (0, 54, arithmetic_constraints),
+          "Arithmetic": (0, 54, arithmetic_constraints), "Cpu": (1, 259, cpu_table_constraints),
           "Keccak": (4, 2431, keccak_constraints),
           "Poseidon": (2, 262, poseidon_constraints),
           "KeccakSponge": (5, 470, keccak_sponge_constraints), "PoseidonSponge": (3, 110, poseidon_sponge_constraints),
           "ShaExtend": (6, 78, sha_extend_constraints), "ShaExtendSponge": (7, 76, sha_extend_sponge_constraints),
           "ShaCompressSponge": (9, 127, sha_compress_sponge_constraints)}
+
+
+def test_all_twelve_tables_are_covered():
+    assert sorted(TABLES) == sorted(t["table"] for t in FIX["tables"]) and len(TABLES) == 12
+
+
+@pytest.mark.parametrize("name", sorted(TABLES))
+def test_second_transcription_matches_constraint_by_constraint(orc, name):
+    """Stronger than the fold: every single constraint value of the shared C++ transcription (oracle = product) equals the Python
+    one at the same position, on the fingerprint frame and on a second frame."""
+    import numpy as np
+    from oracle import binding
+    index, ncols, fn = TABLES[name]
+    for extra in (0, 0x777):
+        seed = FIX["seed"] + 0x10000 * index + extra
+        lv, nv = [splitmix(seed + 2 * c) for c in range(ncols)], [splitmix(seed + 2 * c + 1) for c in range(ncols)]
+
+        class Listing(Consumer):
+            def __init__(self):
+                super().__init__()
+                self.values = []
+
+            def constraint(self, c):
+                self.values.append(c % P)
+                super().constraint(c)
+        yc = Listing()
+        fn(lv, nv, yc)
+        out = np.zeros(1024, dtype=np.uint64)
+        n = orc.orc_table_constraint_values(index, seed, binding.u64ptr(out), out.size)
+        assert n == len(yc.values) == expect(name)["num_constraints"]
+        assert [int(x) for x in out[:n]] == yc.values
 
 
 @pytest.mark.parametrize("name", sorted(TABLES))

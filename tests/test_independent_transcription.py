@@ -656,3 +656,40 @@ def test_second_transcription_reproduces_the_fingerprint(name):
     want = expect(name)
     assert yc.count == want["num_constraints"]
     assert [a % P for a in yc.acc] == want["acc"]
+
+
+# ------------------------------------------------------------------------------------- cross-table and in-table lookups
+def _fold(values):
+    acc = values[0] % P
+    for v in values[1:]:
+        acc = (acc * FIX["alphas"][0] + v) % P
+    return acc
+
+
+def test_second_transcription_of_the_fifteen_ctls():
+    """all_cross_table_lookups() (all_stark.rs:136-542) re-read in tests/ctl_defs_ref.py: the same tables in the same order, the same
+    number of columns, and the fold of (filter, columns...) on each table's fingerprint frame equals the fixture entry by entry --
+    309 entries (294 looking tables + 15 looked tables), 230 of them in the memory CTL."""
+    import ctl_defs_ref as cd
+    ctls = cd.all_cross_table_lookups()
+    assert len(ctls) == len(FIX["ctls"]) == 15
+    checked = 0
+    for (looking, looked), want in zip(ctls, FIX["ctls"]):
+        assert len(looking) == want["num_looking"], want["index"]
+        for e, w in zip(looking + [looked], want["entries"]):
+            assert (e["table"], len(e["columns"])) == (w["table"], w["num_columns"]), (want["index"], w)
+            lv, nv = frame(cd.TABLES.index(e["table"]), cd.NCOLS[e["table"]])
+            assert _fold([e["filter"](lv, nv)] + [c(lv, nv) for c in e["columns"]]) == w["fp"], (want["index"], w)
+            checked += 1
+    assert checked == 309
+
+
+def test_second_transcription_of_the_in_table_lookups():
+    import ctl_defs_ref as cd
+    got = cd.lookups()
+    assert [(t, len(cols)) for t, cols, _t, _f in got] == [(w["table"], w["num_columns"]) for w in FIX["lookups"]]
+    for (table, cols, table_col, freq_col), w in zip(got, FIX["lookups"]):
+        lv, nv = frame(cd.TABLES.index(table), cd.NCOLS[table])
+        # filter_columns = [None; n]: an absent filter evaluates to 1 (lookup.rs: `filter.eval_filter(..)` or ONES)
+        values = [0] + [c(lv, nv) for c in cols] + [table_col(lv, nv), freq_col(lv, nv)] + [1] * len(cols)
+        assert _fold(values) == w["fp"], table

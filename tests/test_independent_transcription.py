@@ -690,6 +690,6 @@ def test_second_transcription_of_the_in_table_lookups():
     assert [(t, len(cols)) for t, cols, _t, _f in got] == [(w["table"], w["num_columns"]) for w in FIX["lookups"]]
     for (table, cols, table_col, freq_col), w in zip(got, FIX["lookups"]):
         lv, nv = frame(cd.TABLES.index(table), cd.NCOLS[table])
-        # filter_columns = [None; n]: an absent filter evaluates to 1 (lookup.rs: `filter.eval_filter(..)` or ONES)
+        # filter_columns = [None; n]: an absent filter counts as 1 (cross_table_lookup.rs get_helper_cols / eval_helper_columns)
         values = [0] + [c(lv, nv) for c in cols] + [table_col(lv, nv), freq_col(lv, nv)] + [1] * len(cols)
         assert _fold(values) == w["fp"], table

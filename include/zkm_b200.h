@@ -272,6 +272,37 @@ int zkm_b200_pagetree_split(zkm_pagetree_t* t, const uint32_t* page_indices, con
                             const uint8_t* registers, uint32_t pc, uint8_t* image_id_out, uint8_t* page_hash_root_out, char** err);
 int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t* out, int* present, char** err);
 
+/* The whole of InstrumentedState::split_segment (emulator/src/state.rs:1477-1530) except the step loop that decides WHEN to split:
+ * a zkm_splitter_t owns the hash pages and the `pre_*` bookkeeping of InstrumentedState (:556-596; all zero at creation).
+ * zkm_b200_splitter_split(s, state, proof, ..):
+ *   1. update_page_hash over state->dirty_pages (Memory::wtrace[0]) and compute_image_id(state->pc, state->registers) on the device;
+ *   2. if `proof`: the Segment { mem_image = state->read_pages (Memory::rtrace, i.e. get_input_image()), segment_id = pre_segment_id,
+ *      pc = pre_pc, pre_hash_root, pre_image_id, image_id, end_pc = state->pc, step = state->step, page_hash_root, input_stream =
+ *      pre_input, input_stream_ptr = pre_input_ptr, public_values_stream = pre_public_values, .. } as its serde_json text in
+ *      *segment_json_out (malloc'ed; zkm_b200_free_string) -- what the reference writes to "{output}/{segment_id}" -- and
+ *      pre_segment_id += 1;
+ *   3. pre_input / pre_public_values / pre_pc / pre_image_id / pre_hash_root take the current values.
+ * split_prog_into_segs (emulator/src/utils.rs:23-57) calls it once with proof = 0 before the first step and with proof = 1 at
+ * every boundary and at exit.  Page indices must be strictly ascending (BTreeMap order). */
+typedef struct zkm_splitter zkm_splitter_t;
+typedef struct {
+    const uint32_t* dirty_page_indices; const uint8_t* dirty_pages; size_t n_dirty_pages;      /* wtrace[0] */
+    const uint32_t* read_page_indices; const uint8_t* read_pages; size_t n_read_pages;         /* rtrace */
+    const uint8_t* registers;                                                                   /* get_registers_bytes(): 156 B */
+    uint32_t pc;
+    uint64_t step;
+    const uint8_t* const* input_stream; const size_t* input_stream_lens; size_t n_input_streams;
+    uint64_t input_stream_ptr;
+    const uint8_t* public_values_stream; size_t public_values_stream_len;
+    uint64_t public_values_stream_ptr;
+} zkm_split_state_t;
+int zkm_b200_splitter_create(zkm_splitter_t** out, char** err);
+void zkm_b200_splitter_destroy(zkm_splitter_t* s);
+zkm_pagetree_t* zkm_b200_splitter_pagetree(zkm_splitter_t* s);
+uint32_t zkm_b200_splitter_segment_count(const zkm_splitter_t* s);
+int zkm_b200_splitter_split(zkm_splitter_t* s, const zkm_split_state_t* state, int proof, char** segment_json_out, size_t* segment_json_len,
+                            uint8_t* image_id_out, uint8_t* page_hash_root_out, char** err);
+
 /* ---- column-layout handshake ---------------------------------------------------------------------------------------
  *
  * The constraint kernels address trace columns by index.  Those indices are the memory layout of the reference's column

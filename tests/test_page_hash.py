@@ -127,3 +127,40 @@ def test_device_page_hashing_matches_oracle(zkm, orc):
             assert (dev.page(hp) == cpu.page(hp)).all(), hex(hp)
     assert dev.page(0x12345) is None
     dev.close(); cpu.close()
+
+
+@pytest.mark.gpu
+def test_splitter_follows_split_segment(zkm, orc):
+    """zkm_b200_splitter_split against a Python model of InstrumentedState::split_segment (emulator/src/state.rs:1477-1530) built on
+    the oracle's page tree: as split_prog_into_segs drives it (utils.rs:23-57) -- one call with proof = false, then boundaries with
+    proof = true.  Every segment file must be the serde_json text of the reference's Segment, image ids and roots must chain."""
+    import json
+    from zkm_b200 import lib as zl
+    rng = np.random.default_rng(23)
+    dev, cpu = zl.Splitter(zkm), binding.OrcPageTree(orc)
+    pre = dict(segment_id=0, pc=0, image_id=bytes(32), hash_root=bytes(32), input=[], input_ptr=0, pv=b"", pv_ptr=0)
+    streams, pv = [b"abc", bytes(range(20))], b""
+    for k, (idx, pages, regs, pc) in enumerate(_segments(29, (12, 30, 7, 50))):
+        proof = k > 0
+        read_idx = sorted(set(idx[::2] + [0x7FFFD, 0x7FFFE]))
+        read_pages = rng.integers(0, 256, size=(len(read_idx), 4096), dtype=np.uint8)
+        step, in_ptr, pv_ptr = 1000 * k + 17, k, 4 * k
+        pv = pv + bytes([k] * 4)
+        text, image_id, root = dev.split((idx, pages), (read_idx, read_pages), regs, pc, step, streams, in_ptr, pv, pv_ptr, proof)
+        want_id, want_root = cpu.split(idx, pages, regs, pc)
+        assert (image_id, root) == (want_id, want_root)
+        if proof:
+            image = {str((pi << 12) + 4 * i): int.from_bytes(read_pages[j, 4 * i:4 * i + 4].tobytes(), "little") for j, pi in enumerate(read_idx)
+                     for i in range(1024)}
+            want = {"mem_image": image, "pc": pre["pc"], "segment_id": pre["segment_id"], "pre_image_id": list(pre["image_id"]),
+                    "pre_hash_root": list(pre["hash_root"]), "image_id": list(want_id), "page_hash_root": list(want_root), "end_pc": pc, "step": step,
+                    "input_stream": [list(b) for b in pre["input"]], "input_stream_ptr": pre["input_ptr"], "public_values_stream": list(pre["pv"]),
+                    "public_values_stream_ptr": pre["pv_ptr"]}
+            assert text.decode() == json.dumps(want, separators=(",", ":"))
+            pre["segment_id"] += 1
+        else:
+            assert text is None
+        pre.update(pc=pc, image_id=want_id, hash_root=want_root, input=list(streams), input_ptr=in_ptr, pv=pv, pv_ptr=pv_ptr)
+        streams = streams + [bytes([k])]
+    assert dev.segment_count() == 3
+    dev.close(); cpu.close()

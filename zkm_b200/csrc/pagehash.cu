@@ -125,6 +125,8 @@ struct PageTreeDev {
 // ---- C ABI (include/zkm_b200.h, "emulator segment splitter") -------------------------------------------------------
 #include "../../include/zkm_b200.h"
 #include <cstdlib>
+#include <string>
+#include <vector>
 
 static int pagehash_fail(char** err, const std::exception& e) {
     if (err) {
@@ -168,6 +170,74 @@ int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t
     auto it = t->t.hash_pages.find(page_index);
     *present = it != t->t.hash_pages.end();
     if (*present) memcpy(out, it->second.data(), zkm::PAGE_BYTES);
+    ZKM_API_END
+}
+
+// ---- the whole split_segment (emulator/src/state.rs:1477-1530) but the step loop: hashing on the device, the pre_* bookkeeping of
+// InstrumentedState (:556-596) and the segment file.
+struct zkm_splitter {
+    zkm_pagetree tree;
+    uint32_t pre_segment_id = 0, pre_pc = 0;
+    uint8_t pre_image_id[32] = {0}, pre_hash_root[32] = {0};
+    std::vector<std::vector<uint8_t>> pre_input;
+    uint64_t pre_input_ptr = 0;
+    std::vector<uint8_t> pre_public_values;
+    uint64_t pre_public_values_ptr = 0;
+};
+
+int zkm_b200_splitter_create(zkm_splitter_t** out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(out, "null argument");
+    *out = new zkm_splitter;
+    ZKM_API_END
+}
+void zkm_b200_splitter_destroy(zkm_splitter_t* s) { delete s; }
+zkm_pagetree_t* zkm_b200_splitter_pagetree(zkm_splitter_t* s) { return s ? &s->tree : nullptr; }
+uint32_t zkm_b200_splitter_segment_count(const zkm_splitter_t* s) { return s ? s->pre_segment_id : 0; }
+
+int zkm_b200_splitter_split(zkm_splitter_t* s, const zkm_split_state_t* st, int proof, char** segment_json_out, size_t* segment_json_len,
+                            uint8_t* image_id_out, uint8_t* page_hash_root_out, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(s && st && image_id_out && page_hash_root_out, "null argument");
+    ZKM_CHECK(!proof || segment_json_out, "null argument");
+    ZKM_CHECK((st->input_stream && st->input_stream_lens) || st->n_input_streams == 0, "null input stream");
+    ZKM_CHECK(st->public_values_stream || st->public_values_stream_len == 0, "null public values stream");
+    uint8_t image_id[32], root[32];
+    // update_page_hash over wtrace[0], then compute_image_id(pc, registers)
+    s->tree.t.split(st->dirty_page_indices, st->dirty_pages, st->n_dirty_pages, st->registers, st->pc, image_id, root, zkm::ctx().stream);
+    if (segment_json_out) *segment_json_out = nullptr;
+    if (proof) {
+        // Segment { mem_image: get_input_image(), segment_id: pre_segment_id, pc: pre_pc, pre_hash_root, pre_image_id, image_id,
+        //           end_pc: pc, step, page_hash_root, input_stream: pre_input, .. } written as serde_json (:1498-1519)
+        std::vector<const uint8_t*> ptrs;
+        std::vector<size_t> lens;
+        for (auto& v : s->pre_input) { ptrs.push_back(v.data()); lens.push_back(v.size()); }
+        zkm_segment_t seg = {};
+        seg.page_indices = st->read_page_indices; seg.pages = st->read_pages; seg.n_pages = st->n_read_pages;
+        seg.pc = s->pre_pc; seg.segment_id = s->pre_segment_id;
+        memcpy(seg.pre_image_id, s->pre_image_id, 32); memcpy(seg.pre_hash_root, s->pre_hash_root, 32);
+        memcpy(seg.image_id, image_id, 32); memcpy(seg.page_hash_root, root, 32);
+        seg.end_pc = st->pc; seg.step = st->step;
+        seg.input_stream = ptrs.data(); seg.input_stream_lens = lens.data(); seg.n_input_streams = ptrs.size();
+        seg.input_stream_ptr = s->pre_input_ptr;
+        seg.public_values_stream = s->pre_public_values.data(); seg.public_values_stream_len = s->pre_public_values.size();
+        seg.public_values_stream_ptr = s->pre_public_values_ptr;
+        char* jerr = nullptr;
+        if (zkm_b200_segment_json(&seg, segment_json_out, segment_json_len, &jerr) != 0) {
+            std::string m = jerr ? jerr : "segment json failed";
+            if (jerr) zkm_b200_free_string(jerr);
+            throw std::runtime_error(m);
+        }
+        s->pre_segment_id += 1;
+    }
+    s->pre_input.assign(st->n_input_streams, {});
+    for (size_t k = 0; k < st->n_input_streams; k++) s->pre_input[k].assign(st->input_stream[k], st->input_stream[k] + st->input_stream_lens[k]);
+    s->pre_input_ptr = st->input_stream_ptr;
+    s->pre_public_values.assign(st->public_values_stream, st->public_values_stream + st->public_values_stream_len);
+    s->pre_public_values_ptr = st->public_values_stream_ptr;
+    s->pre_pc = st->pc;
+    memcpy(s->pre_image_id, image_id, 32); memcpy(s->pre_hash_root, root, 32);
+    memcpy(image_id_out, image_id, 32); memcpy(page_hash_root_out, root, 32);
     ZKM_API_END
 }
 

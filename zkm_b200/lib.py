@@ -38,6 +38,7 @@ EXPORTS = [
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
     "zkm_b200_stage_table", "zkm_b200_segment_json", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
+    "zkm_b200_splitter_create", "zkm_b200_splitter_destroy", "zkm_b200_splitter_pagetree", "zkm_b200_splitter_segment_count", "zkm_b200_splitter_split",
 ]
 
 
@@ -496,3 +497,59 @@ def segment_json(lib, page_indices, pages, pc, segment_id, pre_image_id, pre_has
     text = C.string_at(out, n.value)
     lib.zkm_b200_free_string(out)
     return text
+
+
+class SplitState(C.Structure):
+    _fields_ = [("dirty_page_indices", C.c_void_p), ("dirty_pages", C.c_void_p), ("n_dirty_pages", C.c_size_t),
+                ("read_page_indices", C.c_void_p), ("read_pages", C.c_void_p), ("n_read_pages", C.c_size_t), ("registers", C.c_char_p),
+                ("pc", C.c_uint32), ("step", C.c_uint64), ("input_stream", C.POINTER(C.c_char_p)), ("input_stream_lens", C.POINTER(C.c_size_t)),
+                ("n_input_streams", C.c_size_t), ("input_stream_ptr", C.c_uint64), ("public_values_stream", C.c_char_p),
+                ("public_values_stream_len", C.c_size_t), ("public_values_stream_ptr", C.c_uint64)]
+
+
+class Splitter:
+    """zkm_splitter_t: InstrumentedState::split_segment (hashing on the device, pre_* bookkeeping, segment file text)."""
+
+    def __init__(self, lib):
+        self.lib, self.h = lib, C.c_void_p()
+        err = C.c_void_p()
+        lib.zkm_b200_splitter_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        lib.zkm_b200_splitter_destroy.argtypes = [C.c_void_p]
+        lib.zkm_b200_splitter_segment_count.argtypes = [C.c_void_p]
+        lib.zkm_b200_splitter_segment_count.restype = C.c_uint32
+        lib.zkm_b200_splitter_split.argtypes = [C.c_void_p, C.POINTER(SplitState), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p,
+                                                C.c_void_p, C.POINTER(C.c_void_p)]
+        check(lib, lib.zkm_b200_splitter_create(C.byref(self.h), C.byref(err)), err)
+
+    def split(self, dirty, read, registers: bytes, pc: int, step: int, input_stream, input_stream_ptr, public_values_stream, public_values_stream_ptr,
+              proof: bool):
+        """dirty / read = (ascending page indices, (n, 4096) uint8).  Returns (segment json bytes or None, image id, page hash root)."""
+        di, dp = np.ascontiguousarray(dirty[0], dtype=np.uint32), np.ascontiguousarray(dirty[1], dtype=np.uint8).reshape(-1, 4096)
+        ri, rp = np.ascontiguousarray(read[0], dtype=np.uint32), np.ascontiguousarray(read[1], dtype=np.uint8).reshape(-1, 4096)
+        st = SplitState()
+        st.dirty_page_indices, st.dirty_pages, st.n_dirty_pages = di.ctypes.data, dp.ctypes.data, di.size
+        st.read_page_indices, st.read_pages, st.n_read_pages = ri.ctypes.data, rp.ctypes.data, ri.size
+        st.registers, st.pc, st.step = registers, pc, step
+        streams = [bytes(b) for b in input_stream]
+        arr = (C.c_char_p * max(1, len(streams)))(*streams)
+        lens = (C.c_size_t * max(1, len(streams)))(*[len(b) for b in streams])
+        st.input_stream, st.input_stream_lens, st.n_input_streams, st.input_stream_ptr = arr, lens, len(streams), input_stream_ptr
+        pvs = bytes(public_values_stream)
+        st.public_values_stream, st.public_values_stream_len, st.public_values_stream_ptr = pvs, len(pvs), public_values_stream_ptr
+        out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        image_id, root = np.zeros(32, dtype=np.uint8), np.zeros(32, dtype=np.uint8)
+        check(self.lib, self.lib.zkm_b200_splitter_split(self.h, C.byref(st), int(proof), C.byref(out), C.byref(n), image_id.ctypes.data,
+                                                         root.ctypes.data, C.byref(err)), err)
+        text = None
+        if out.value:
+            text = C.string_at(out, n.value)
+            self.lib.zkm_b200_free_string(out)
+        return text, bytes(image_id), bytes(root)
+
+    def segment_count(self):
+        return self.lib.zkm_b200_splitter_segment_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.zkm_b200_splitter_destroy(self.h)
+            self.h = C.c_void_p()

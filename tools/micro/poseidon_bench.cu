@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(128, MINB) k_v9_x2(const u64* __restrict__ in,
     for (int k = 0; k < 12; k++) { out[k * count + i] = a[k]; out[k * count + half + i] = b[k]; }
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool quick = argc > 1;                  // only the product configuration (A/B builds of one knob)
     const size_t count = 1 << 20;
     const int reps = 8;
     std::vector<u64> h(12 * count);
@@ -83,8 +84,9 @@ int main() {
         printf("%-40s %s %8.3f ms -> %.3f Gperm/s  mismatches=%zu\n", name, cudaGetErrorString(e), best, count * reps / (best * 1e-3) / 1e9, bad);
     };
     const unsigned g = (unsigned)(count / 128);
-    printf("ZKM_P9_SBOX_UNROLL=%d\n", ZKM_P9_SBOX_UNROLL);
+    printf("ZKM_P9_SBOX_UNROLL=%d ZKM_P9_MULMIX=%d\n", ZKM_P9_SBOX_UNROLL, ZKM_P9_MULMIX);
     run("v9 cv3 lb(128,8)  [product]", [&] { k_v9<8, 3><<<g, 128>>>(din, dout, count, reps); });
+    if (quick) { run("v9 cv3 lb(128,6)", [&] { k_v9<6, 3><<<g, 128>>>(din, dout, count, reps); }); return 0; }
     run("v9 cv3 lb(128,6)", [&] { k_v9<6, 3><<<g, 128>>>(din, dout, count, reps); });
     run("v9 cv3 lb(128,4)", [&] { k_v9<4, 3><<<g, 128>>>(din, dout, count, reps); });
     run("v9 cv0 lb(128,8)", [&] { k_v9<8, 0><<<g, 128>>>(din, dout, count, reps); });

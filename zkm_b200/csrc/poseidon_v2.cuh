@@ -64,11 +64,37 @@ __device__ __forceinline__ u64 p9_mul(u64 a, u64 b) {
         : "=r"(o0), "=r"(o1) : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
     return (u64)o0 | ((u64)o1 << 32);
 }
+// The same multiply with the 128-bit product written in PTX (4 mul.wide + two add.cc chains): its carry handling lands on the ALU
+// pipe (IADD3 / IADD3.X) where the compiler's own product uses IMAD.X / IMAD.MOV on the port DFMA and IMAD.WIDE share (DESIGN.md
+// section 3).  ZKM_P9_MULMIX selects, per multiply of the S-box (bit 0: x*x, 1: x2*x, 2: x2*x2, 3: x3*x4), which product is used;
+// 0 = the compiler's everywhere (the product build).  A/B knob of tools/micro/poseidon_bench.cu.
+#ifndef ZKM_P9_MULMIX
+#define ZKM_P9_MULMIX 0
+#endif
+__device__ __forceinline__ u64 p9_mul_ptx(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 o0, o1;
+    asm("{\n\t.reg .u64 p00,p01,p10,p11;\n\t.reg .u32 r0,r1,r2,r3,t1,u1,u2,v1,v2,w2,w3,s0,s1,t0,tt1,b,c,m;\n\t"
+        "mul.wide.u32 p00, %2, %4;\n\tmul.wide.u32 p01, %2, %5;\n\tmul.wide.u32 p10, %3, %4;\n\tmul.wide.u32 p11, %3, %5;\n\t"
+        "mov.b64 {r0, t1}, p00;\n\tmov.b64 {u1, u2}, p01;\n\tmov.b64 {v1, v2}, p10;\n\tmov.b64 {w2, w3}, p11;\n\t"
+        "add.cc.u32 r1, t1, u1;\n\taddc.cc.u32 r2, u2, w2;\n\taddc.u32 r3, w3, 0;\n\t"
+        "add.cc.u32 r1, r1, v1;\n\taddc.cc.u32 r2, r2, v2;\n\taddc.u32 r3, r3, 0;\n\t"
+        "add.cc.u32 s0, r2, r3;\n\taddc.u32 s1, 0, 0;\n\t"
+        "sub.cc.u32 t0, r0, s0;\n\tsubc.cc.u32 tt1, r1, s1;\n\tsubc.u32 b, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, b;\n\tsubc.u32 tt1, tt1, 0;\n\t"
+        "add.cc.u32 tt1, tt1, r2;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, t0, m;\n\taddc.u32 %1, tt1, 0;\n\t}"
+        : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return (u64)o0 | ((u64)o1 << 32);
+}
+template <int BIT>
+__device__ __forceinline__ u64 p9_mul_sel(u64 a, u64 b) { return ((ZKM_P9_MULMIX >> BIT) & 1) ? p9_mul_ptx(a, b) : p9_mul(a, b); }
 __device__ __forceinline__ u64 p9_sbox7(u64 x) {
-    u64 x2 = p9_mul(x, x);
-    u64 x3 = p9_mul(x2, x);
-    u64 x4 = p9_mul(x2, x2);
-    return p9_mul(x3, x4);
+    u64 x2 = p9_mul_sel<0>(x, x);
+    u64 x3 = p9_mul_sel<1>(x2, x);
+    u64 x4 = p9_mul_sel<2>(x2, x2);
+    return p9_mul_sel<3>(x3, x4);
 }
 // exact integer MDS on 12 doubles (one 32-bit half of every state word, or an unreduced half from the previous layer)
 __device__ __forceinline__ void p9_mds_half(const double* x, double* o) {

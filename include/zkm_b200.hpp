@@ -277,4 +277,130 @@ inline std::string public_values_json(const AllProof& ap) {
     return s;
 }
 
+// ---- proving straight from the witness (`Traces`, witness/traces.rs:46-60): every table but Cpu crosses the ABI as its operation
+// log and is generated on the device (zkm_b200_prove_with_ops), the Cpu rows go row-major.  The C++ counterpart of shim/src/b200_ops.rs.
+struct MemoryAddress { uint64_t context = 0, segment = 0, virt = 0; };                     // witness/memory.rs:27-31
+enum class MemoryOpKind { Read, Write };
+struct MemoryOp { bool filter = true; uint64_t timestamp = 0; MemoryAddress address; MemoryOpKind kind = MemoryOpKind::Read; uint32_t value = 0; };
+struct ArithmeticOperation { uint32_t row_filter = 0, input0 = 0, input1 = 0; };            // BinaryOperator::row_filter() = the IS_* column
+enum class LogicOp : uint32_t { And = 0, Or, Xor, Nor };                                    // logic.rs:84-89
+struct LogicOperation { LogicOp operator_ = LogicOp::And; uint32_t input0 = 0, input1 = 0; };
+struct SpongeOp { std::vector<MemoryAddress> base_address; uint64_t timestamp = 0; std::vector<uint8_t> input; };   // Keccak / PoseidonSpongeOp
+struct ShaExtendSpongeOp { std::vector<MemoryAddress> base_address; uint64_t timestamp = 0; std::array<uint8_t, 16> input{}; uint32_t i = 0;
+                           MemoryAddress output_address; };
+struct ShaCompressInput { std::array<uint8_t, 41> input{}; MemoryAddress w_i_address; uint64_t timestamp = 0; };    // one ROW of ShaCompress
+struct ShaCompressSpongeOp { std::vector<MemoryAddress> base_address; uint64_t timestamp = 0; std::array<uint8_t, 32> input{};
+                             std::vector<std::array<uint8_t, 4>> w_i_s; };
+struct Traces {
+    std::vector<ArithmeticOperation> arithmetic_ops;
+    std::vector<F> cpu;                                                                       // rows x 259, row-major, padded to a power of two
+    std::vector<LogicOperation> logic_ops;
+    std::vector<MemoryOp> memory_ops;
+    std::vector<std::pair<std::array<F, 12>, uint64_t>> poseidon_inputs;
+    std::vector<SpongeOp> poseidon_sponge_ops;
+    std::vector<std::pair<std::array<uint64_t, 25>, uint64_t>> keccak_inputs;
+    std::vector<SpongeOp> keccak_sponge_ops;
+    std::vector<std::pair<std::array<uint8_t, 16>, uint64_t>> sha_extend_inputs;
+    std::vector<ShaExtendSpongeOp> sha_extend_sponge_ops;
+    std::vector<ShaCompressInput> sha_compress_inputs;
+    std::vector<ShaCompressSpongeOp> sha_compress_sponge_ops;
+};
+struct OpLog { std::vector<uint64_t> words; size_t n_ops = 0; };
+
+namespace detail {
+inline uint64_t le_u32(const uint8_t* b) { return (uint64_t)b[0] | (uint64_t)b[1] << 8 | (uint64_t)b[2] << 16 | (uint64_t)b[3] << 24; }
+inline OpLog sponge_log(const std::vector<SpongeOp>& ops) {
+    OpLog log;
+    log.words.push_back(0);
+    for (const SpongeOp& op : ops) {
+        if (op.base_address.empty()) throw Error("sponge operation without addresses");
+        for (uint64_t w : {op.base_address[0].context, op.base_address[0].segment, op.timestamp, (uint64_t)op.input.size(), (uint64_t)op.base_address.size()})
+            log.words.push_back(w);
+        for (const MemoryAddress& a : op.base_address) log.words.push_back(a.virt);
+        for (size_t i = 0; i < op.input.size(); i += 8) {
+            uint64_t w = 0;
+            for (size_t j = 0; j < 8 && i + j < op.input.size(); j++) w |= (uint64_t)op.input[i + j] << (8 * j);
+            log.words.push_back(w);
+        }
+        log.n_ops++;
+    }
+    log.words[0] = log.words.size();
+    return log;
+}
+}  // namespace detail
+
+// The eleven operation logs, indexed by `Table` (formats: zkm_b200.h next to zkm_op_log_t); logs[Cpu] stays empty.
+inline std::array<OpLog, NUM_TABLES> op_logs(const Traces& t) {
+    std::array<OpLog, NUM_TABLES> logs;
+    auto at = [&](Table x) -> OpLog& { return logs[(size_t)x]; };
+    for (auto& o : t.arithmetic_ops) { auto& l = at(Table::Arithmetic); l.words.insert(l.words.end(), {o.row_filter, o.input0, o.input1}); l.n_ops++; }
+    for (auto& o : t.logic_ops) { auto& l = at(Table::Logic); l.words.insert(l.words.end(), {(uint64_t)o.operator_, o.input0, o.input1}); l.n_ops++; }
+    for (auto& m : t.memory_ops) {
+        auto& l = at(Table::Memory);
+        l.words.insert(l.words.end(), {m.address.context, m.address.segment, m.address.virt, m.timestamp, (uint64_t)(m.kind == MemoryOpKind::Read), m.value,
+                                       (uint64_t)m.filter});
+        l.n_ops++;
+    }
+    for (auto& p : t.poseidon_inputs) { auto& l = at(Table::Poseidon); l.words.insert(l.words.end(), p.first.begin(), p.first.end()); l.words.push_back(p.second); l.n_ops++; }
+    for (auto& k : t.keccak_inputs) { auto& l = at(Table::Keccak); l.words.insert(l.words.end(), k.first.begin(), k.first.end()); l.words.push_back(k.second); l.n_ops++; }
+    at(Table::PoseidonSponge) = detail::sponge_log(t.poseidon_sponge_ops);
+    at(Table::KeccakSponge) = detail::sponge_log(t.keccak_sponge_ops);
+    for (auto& e : t.sha_extend_inputs) {
+        auto& l = at(Table::ShaExtend);
+        for (int k = 0; k < 4; k++) l.words.push_back(detail::le_u32(e.first.data() + 4 * k));
+        l.words.push_back(e.second); l.n_ops++;
+    }
+    for (auto& o : t.sha_extend_sponge_ops) {
+        auto& l = at(Table::ShaExtendSponge);
+        if (o.base_address.size() < 4) throw Error("sha extend sponge operation needs four addresses");
+        l.words.push_back(o.i);
+        for (int k = 0; k < 4; k++) l.words.push_back(detail::le_u32(o.input.data() + 4 * k));
+        for (int k = 0; k < 4; k++) l.words.push_back(o.base_address[k].virt);
+        l.words.insert(l.words.end(), {o.output_address.virt, o.base_address[0].context, o.base_address[0].segment, o.timestamp});
+        l.n_ops++;
+    }
+    for (auto& r : t.sha_compress_inputs) {
+        auto& l = at(Table::ShaCompress);
+        for (int k = 0; k < 10; k++) l.words.push_back(detail::le_u32(r.input.data() + 4 * k));
+        l.words.insert(l.words.end(), {(uint64_t)r.input[40], r.w_i_address.virt, r.w_i_address.segment, r.w_i_address.context, r.timestamp});
+        l.n_ops++;
+    }
+    for (auto& o : t.sha_compress_sponge_ops) {
+        auto& l = at(Table::ShaCompressSponge);
+        if (o.base_address.size() < 9 || o.w_i_s.size() != 64) throw Error("sha compress sponge operation needs nine addresses and 64 message words");
+        for (int k = 0; k < 8; k++) l.words.push_back(detail::le_u32(o.input.data() + 4 * k));
+        for (auto& w : o.w_i_s) l.words.push_back(detail::le_u32(w.data()));
+        for (int k = 0; k < 8; k++) l.words.push_back(o.base_address[k].virt);
+        const MemoryAddress& ws = o.base_address[8];
+        l.words.insert(l.words.end(), {ws.virt, ws.segment, ws.context, o.base_address[0].context, o.base_address[0].segment, o.timestamp});
+        l.n_ops++;
+    }
+    return logs;
+}
+
+// Traces::into_tables + prove_with_traces in one device-side call (prover.rs:58-128 call chain).
+inline AllProof prove_from_traces(const StarkConfig& config, const Traces& traces, const PublicValues& public_values) {
+    constexpr uint32_t CPU_COLUMNS = 259;
+    const size_t rows = traces.cpu.size() / CPU_COLUMNS;
+    if (rows * CPU_COLUMNS != traces.cpu.size() || rows < 64 || (rows & (rows - 1))) throw Error("the Cpu rows must be padded to a power of two");
+    uint32_t log_n = 0;
+    while (((size_t)1 << log_n) < rows) log_n++;
+    std::array<OpLog, NUM_TABLES> logs = op_logs(traces);
+    zkm_table_t tables[NUM_TABLES] = {};
+    zkm_table_rows_t row_tables[NUM_TABLES] = {};
+    zkm_op_log_t c_logs[NUM_TABLES] = {};
+    row_tables[(size_t)Table::Cpu] = zkm_table_rows_t{traces.cpu.data(), CPU_COLUMNS, log_n};
+    static const uint64_t empty_log = 0;
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        if (t == (size_t)Table::Cpu) continue;
+        c_logs[t].ops = logs[t].words.empty() ? &empty_log : logs[t].words.data();        // a non-null pointer selects the device generator
+        c_logs[t].n_ops = logs[t].n_ops;
+    }
+    uint64_t* out = nullptr; size_t words = 0; char* err = nullptr;
+    detail::check(zkm_b200_prove_with_ops(tables, row_tables, c_logs, public_values.roots_before.root.data(), public_values.roots_after.root.data(),
+                                          public_values.userdata.data(), (uint32_t)public_values.userdata.size(), &config.c, &out, &words, &err), err);
+    struct Free { uint64_t* p; ~Free() { zkm_b200_free(p); } } guard{out};
+    return decode_all_proof(out, words);
+}
+
 }  // namespace zkm_b200

@@ -3,6 +3,8 @@
 //   host_mirror decode <proof.bin> <table>          CPU: decode -> re-encode round trip, shape summary, JSON of one table
 //   host_mirror prove <out.bin> <log heights x 12>  GPU: prove_with_traces over the synthetic traces, proof written to <out.bin>
 //   host_mirror errors                              CPU: the error paths that need no device
+//   host_mirror oplogs <traces.bin> <logs.bin>      CPU: a typed `Traces` (dumped by the test, one field per word) -> op_logs() ->
+//                                                   per table: n_ops, words, the words
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -20,9 +22,71 @@ static std::vector<uint64_t> read_words(const char* path) {
     return w;
 }
 
+// The typed Traces dump of tests/test_cpp_host.py: every scalar one word, every byte one word, sections in `Traces` field order.
+struct Words {
+    std::vector<uint64_t> w; size_t at = 0;
+    uint64_t next() { if (at >= w.size()) throw Error("traces dump truncated"); return w[at++]; }
+    MemoryAddress addr() { MemoryAddress a; a.context = next(); a.segment = next(); a.virt = next(); return a; }
+    std::vector<MemoryAddress> addrs() { std::vector<MemoryAddress> v(next()); for (auto& a : v) a = addr(); return v; }
+    template <size_t N> std::array<uint8_t, N> bytes() { std::array<uint8_t, N> b; for (auto& x : b) x = (uint8_t)next(); return b; }
+};
+static Traces read_traces(const char* path) {
+    Words in{read_words(path)};
+    Traces t;
+    t.arithmetic_ops.resize(in.next());
+    for (auto& o : t.arithmetic_ops) { o.row_filter = (uint32_t)in.next(); o.input0 = (uint32_t)in.next(); o.input1 = (uint32_t)in.next(); }
+    t.logic_ops.resize(in.next());
+    for (auto& o : t.logic_ops) { o.operator_ = (LogicOp)in.next(); o.input0 = (uint32_t)in.next(); o.input1 = (uint32_t)in.next(); }
+    t.memory_ops.resize(in.next());
+    for (auto& m : t.memory_ops) {
+        m.address = in.addr(); m.timestamp = in.next(); m.kind = in.next() ? MemoryOpKind::Read : MemoryOpKind::Write;
+        m.value = (uint32_t)in.next(); m.filter = in.next() != 0;
+    }
+    t.poseidon_inputs.resize(in.next());
+    for (auto& p : t.poseidon_inputs) { for (auto& x : p.first) x = in.next(); p.second = in.next(); }
+    for (auto* ops : {&t.poseidon_sponge_ops, &t.keccak_sponge_ops}) {
+        ops->resize(in.next());
+        for (auto& o : *ops) { o.base_address = in.addrs(); o.timestamp = in.next(); o.input.resize(in.next()); for (auto& b : o.input) b = (uint8_t)in.next(); }
+    }
+    t.keccak_inputs.resize(in.next());
+    for (auto& k : t.keccak_inputs) { for (auto& x : k.first) x = in.next(); k.second = in.next(); }
+    t.sha_extend_inputs.resize(in.next());
+    for (auto& e : t.sha_extend_inputs) { e.first = in.bytes<16>(); e.second = in.next(); }
+    t.sha_extend_sponge_ops.resize(in.next());
+    for (auto& o : t.sha_extend_sponge_ops) { o.base_address = in.addrs(); o.timestamp = in.next(); o.input = in.bytes<16>(); o.i = (uint32_t)in.next(); o.output_address = in.addr(); }
+    t.sha_compress_inputs.resize(in.next());
+    for (auto& r : t.sha_compress_inputs) { r.input = in.bytes<41>(); r.w_i_address = in.addr(); r.timestamp = in.next(); }
+    t.sha_compress_sponge_ops.resize(in.next());
+    for (auto& o : t.sha_compress_sponge_ops) {
+        o.base_address = in.addrs(); o.timestamp = in.next(); o.input = in.bytes<32>();
+        o.w_i_s.resize(in.next());
+        for (auto& w : o.w_i_s) w = in.bytes<4>();
+    }
+    if (in.at != in.w.size()) throw Error("traces dump has trailing words");
+    return t;
+}
+
 int main(int argc, char** argv) {
     try {
         const std::string mode = argc > 1 ? argv[1] : "";
+        if (mode == "oplogs" && argc == 4) {
+            Traces t = read_traces(argv[2]);
+            std::array<OpLog, NUM_TABLES> logs = op_logs(t);
+            std::ofstream out(argv[3], std::ios::binary);
+            for (const OpLog& l : logs) {
+                const uint64_t head[2] = {l.n_ops, l.words.size()};
+                out.write((const char*)head, 16);
+                out.write((const char*)l.words.data(), (std::streamsize)(l.words.size() * 8));
+            }
+            // the shape errors of the typed operations are reported, not undefined behaviour
+            Traces bad = t;
+            bad.sha_compress_sponge_ops.emplace_back();
+            try { op_logs(bad); std::puts("SHORT OP NOT DETECTED"); return 1; } catch (const Error& e) { std::printf("short: %s\n", e.what()); }
+            bad = Traces{};
+            bad.cpu.assign(259 * 48, 0);
+            try { prove_from_traces(StarkConfig::standard_fast_config(), bad, PublicValues{}); return 1; } catch (const Error& e) { std::printf("cpu: %s\n", e.what()); }
+            return 0;
+        }
         if (mode == "decode" && argc == 4) {
             std::vector<uint64_t> buf = read_words(argv[2]);
             AllProof ap = decode_all_proof(buf.data(), buf.size());

@@ -106,6 +106,15 @@ int main(int argc, char** argv) {
             std::printf("PV %s\n", public_values_json(ap).c_str());
             // a truncated buffer is an error, not a crash
             try { decode_all_proof(buf.data(), buf.size() - 5); std::puts("TRUNCATION NOT DETECTED"); return 1; } catch (const Error& e) { std::printf("truncated: %s\n", e.what()); }
+            // lengths come from the buffer: counts whose byte size wraps must be errors as well (any word of the first table)
+            size_t refused = 0;
+            for (size_t at = 2; at < std::min<size_t>(buf.size(), 1500); at++)
+                for (uint64_t k : {~0ULL, 1ULL << 63, 1ULL << 62, (1ULL << 61) + 3}) {
+                    std::vector<uint64_t> bad = buf;
+                    bad[at] = k;
+                    try { decode_all_proof(bad.data(), bad.size()); } catch (const std::exception&) { refused++; }
+                }
+            std::printf("hostile lengths refused: %zu\n", refused);
             return 0;
         }
         if (mode == "prove" && argc == 3 + (int)NUM_TABLES) {

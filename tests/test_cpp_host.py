@@ -54,6 +54,8 @@ def test_cpp_decodes_an_all_stark_proof(exe, orc, tmp_path):
     pv = json.loads([l for l in lines if l.startswith("PV ")][0][3:])
     assert pv["userdata"] == [0] * 32
     assert "truncated: proof buffer truncated" in out
+    refused = int([l for l in lines if l.startswith("hostile lengths refused: ")][0].split(": ")[1])
+    assert refused >= 4 * 12                                 # at least the header counts and the first table's vec lengths
     err = _run(exe, "errors")
     assert "config 2 4 16 37 2 4 5" in err and "junk: bad proof magic" in err and "empty: null/empty table" in err
 

@@ -95,6 +95,55 @@ def test_json_errors():
     lib.zkm_b200_free_string(err)
 
 
+def test_hostile_proof_buffers_are_errors_not_crashes(orc):
+    """Every length in the flat buffer comes from the buffer: counts chosen so that `pos + k` or `k * unit` wraps, counts far
+    beyond the buffer and every truncation must come back as an error from both JSON entry points."""
+    import ctypes as C
+    lib = zl.load()
+    proof = binding.prove_system(orc, tr.SYSTEM_LOGIC, [tr.logic_trace(6)])
+
+    def calls(buf, words=None):
+        buf = np.ascontiguousarray(buf, dtype=np.uint64)
+        words = buf.size if words is None else words
+        rcs = []
+        for fn, args in ((lib.zkm_b200_proof_table_json, (0,)), (lib.zkm_b200_public_values_json, ())):
+            out, n, err = C.c_void_p(), C.c_size_t(), C.c_void_p()
+            rc = fn(zl.u64ptr(buf), C.c_size_t(words), *args, C.byref(out), C.byref(n), C.byref(err))
+            assert rc in (0, -1) and (rc == 0) == (err.value is None)
+            lib.zkm_b200_free_string(err if rc else out)
+            rcs.append(rc)
+        return rcs
+
+    assert calls(proof) == [0, 0]
+    # the length words of the buffer: walk it once to find them (header counts, then every vec length of table 0)
+    r = Walk(proof)
+    r.words(3)
+    at = [r.p]                                   # number of challenges
+    r.words(2 * r.u() + 16)
+    at.append(r.p)                               # userdata length
+    r.vec(1)
+    r.words(12)
+    for unit in (4, 4, 4, 2, 2, 2, 2, 1, 2):
+        at.append(r.p)
+        r.vec(unit)
+    at.append(r.p)                               # number of commit-phase caps
+    hostile = [(1 << 64) - 1, (1 << 63), (1 << 62), (1 << 62) + 1, (1 << 61) + 3, proof.size, 1 << 32]
+    for pos in at:
+        for k in hostile:
+            bad = proof.copy()
+            bad[pos] = k
+            rcs = calls(bad)
+            assert rcs[0] == -1, (pos, k)          # the table walk crosses every one of these counts
+            assert rcs[1] == (-1 if pos in at[:2] else 0)
+    rng = np.random.default_rng(3)
+    for words in sorted({0, 1, 2, 3, 4, 30, proof.size - 1, *rng.integers(5, proof.size - 1, size=40).tolist()}):
+        assert calls(proof, words)[0] == -1
+    for _ in range(200):                         # random single-word corruption: any status, no crash
+        bad = proof.copy()
+        bad[int(rng.integers(0, proof.size))] = int(rng.integers(0, 1 << 63)) << int(rng.integers(0, 2))
+        calls(bad)
+
+
 def test_segment_json_is_the_serde_text_of_the_emulator_segment():
     """zkm_b200_segment_json against Python's own compact JSON of the same structure (emulator/src/state.rs:33-48: field order of
     the struct, BTreeMap<u32, u32> as an object with decimal-string keys in ascending numeric order, [u8; 32] and Vec<u8> as

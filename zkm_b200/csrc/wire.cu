@@ -25,7 +25,11 @@ namespace {
 struct Rd {
     const u64* p; size_t n, pos = 0;
     u64 u() { if (pos >= n) throw std::runtime_error("proof buffer truncated"); return p[pos++]; }
-    const u64* words(size_t k) { if (pos + k > n) throw std::runtime_error("proof buffer truncated"); const u64* r = p + pos; pos += k; return r; }
+    // `k` items of `unit` words; the counts come from the buffer, so neither pos + k nor k * unit may be trusted not to wrap
+    const u64* words(size_t k, size_t unit = 1) {
+        if (k > (n - pos) / unit) throw std::runtime_error("proof buffer truncated");
+        const u64* r = p + pos; pos += k * unit; return r;
+    }
 };
 struct Js {
     std::string s;
@@ -45,27 +49,27 @@ static const u64 MAGIC = 0x464F4F52504D4B5AULL;
 
 void skip_table(Rd& r) {
     r.words(12);
-    for (int c = 0; c < 3; c++) { size_t k = r.u(); r.words(4 * k); }
-    for (int v = 0; v < 4; v++) { size_t k = r.u(); r.words(2 * k); }
+    for (int c = 0; c < 3; c++) { size_t k = r.u(); r.words(k, 4); }
+    for (int v = 0; v < 4; v++) { size_t k = r.u(); r.words(k, 2); }
     { size_t k = r.u(); r.words(k); }
-    { size_t k = r.u(); r.words(2 * k); }
+    { size_t k = r.u(); r.words(k, 2); }
     size_t ncaps = r.u();
-    for (size_t i = 0; i < ncaps; i++) { size_t k = r.u(); r.words(4 * k); }
+    for (size_t i = 0; i < ncaps; i++) { size_t k = r.u(); r.words(k, 4); }
     size_t nq = r.u();
     for (size_t q = 0; q < nq; q++) {
         size_t no = r.u();
-        for (size_t o = 0; o < no; o++) { size_t k = r.u(); r.words(k); k = r.u(); r.words(4 * k); }
+        for (size_t o = 0; o < no; o++) { size_t k = r.u(); r.words(k); k = r.u(); r.words(k, 4); }
         size_t ns = r.u();
-        for (size_t st = 0; st < ns; st++) { size_t k = r.u(); r.words(2 * k); k = r.u(); r.words(4 * k); }
+        for (size_t st = 0; st < ns; st++) { size_t k = r.u(); r.words(k, 2); k = r.u(); r.words(k, 4); }
     }
-    { size_t k = r.u(); r.words(2 * k); }
+    { size_t k = r.u(); r.words(k, 2); }
     r.u();
 }
 
 void vec_field(Rd& r, Js& j, const char* name, int unit) {
     j.key(name);
     size_t k = r.u();
-    const u64* w = r.words(k * unit);
+    const u64* w = r.words(k, (size_t)unit);
     if (unit == 1) j.fs(w, k); else if (unit == 2) j.exts(w, k); else j.hashes(w, k);
 }
 
@@ -86,7 +90,7 @@ void stark_proof_json(Rd& r, Js& j) {
     j.key("opening_proof"); j.s += '{';
     j.key("commit_phase_merkle_caps");
     size_t ncaps = r.u();
-    j.list(ncaps, [&](size_t) { size_t k = r.u(); j.hashes(r.words(4 * k), k); });
+    j.list(ncaps, [&](size_t) { size_t k = r.u(); j.hashes(r.words(k, 4), k); });
     j.s += ',';
     j.key("query_round_proofs");
     size_t nq = r.u();
@@ -98,7 +102,7 @@ void stark_proof_json(Rd& r, Js& j) {
             j.s += '[';
             size_t k = r.u(); j.fs(r.words(k), k);
             j.s += ",{\"siblings\":";
-            k = r.u(); j.hashes(r.words(4 * k), k);
+            k = r.u(); j.hashes(r.words(k, 4), k);
             j.s += "}]";
         });
         j.s += "},";
@@ -106,16 +110,16 @@ void stark_proof_json(Rd& r, Js& j) {
         size_t ns = r.u();
         j.list(ns, [&](size_t) {
             j.s += "{\"evals\":";
-            size_t k = r.u(); j.exts(r.words(2 * k), k);
+            size_t k = r.u(); j.exts(r.words(k, 2), k);
             j.s += ",\"merkle_proof\":{\"siblings\":";
-            k = r.u(); j.hashes(r.words(4 * k), k);
+            k = r.u(); j.hashes(r.words(k, 4), k);
             j.s += "}}";
         });
         j.s += '}';
     });
     j.s += ',';
     j.key("final_poly"); j.s += "{\"coeffs\":";
-    { size_t k = r.u(); j.exts(r.words(2 * k), k); }
+    { size_t k = r.u(); j.exts(r.words(k, 2), k); }
     j.s += "},";
     j.key("pow_witness"); j.num(r.u());
     j.s += "}}";
@@ -137,7 +141,7 @@ size_t read_header(Rd& r, Js* pv) {
     if (r.u() != 1) throw std::runtime_error("bad proof version");
     size_t nt = r.u();
     size_t nch = r.u();
-    r.words(2 * nch);
+    r.words(nch, 2);
     const u64* rb = r.words(8);
     const u64* ra = r.words(8);
     size_t nu = r.u();

@@ -271,6 +271,10 @@ void zkm_b200_pagetree_destroy(zkm_pagetree_t* t);
 int zkm_b200_pagetree_split(zkm_pagetree_t* t, const uint32_t* page_indices, const uint8_t* pages, size_t n_pages,
                             const uint8_t* registers, uint32_t pc, uint8_t* image_id_out, uint8_t* page_hash_root_out, char** err);
 int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t* out, int* present, char** err);
+/* Seeds one hash page (index 0x80000 ..= 0x81020) from the caller's memory: an emulator state resumed from a segment file
+ * (State::load_seg, emulator/src/state.rs:141-190, as split_seg_into_segs does, utils.rs:62-109) carries its hash pages in the
+ * memory image.  Host-only: needs no device. */
+int zkm_b200_pagetree_set_page(zkm_pagetree_t* t, uint32_t page_index, const uint8_t* data, char** err);
 
 /* The whole of InstrumentedState::split_segment (emulator/src/state.rs:1477-1530) except the step loop that decides WHEN to split:
  * a zkm_splitter_t owns the hash pages and the `pre_*` bookkeeping of InstrumentedState (:556-596; all zero at creation).

@@ -5,7 +5,8 @@
 //! permutations per dirty 4 KiB page, on one core) and `serde_json::to_vec(&segment)` become one call of
 //! `zkm_b200_splitter_split` (include/zkm_b200.h).  Needs `pub(crate)` on `Memory::{pages, rtrace, wtrace}` (memory.rs:121-136) and
 //! on the `pre_*` fields of `InstrumentedState` (state.rs:552-560), one `splitter: *mut c_void` field created in
-//! `InstrumentedState::new` with `zkm_b200_splitter_create`, and `zkm_b200_init(0, ..)` once per process.
+//! `InstrumentedState::new` with `splitter_create` (followed by `splitter_seed` when the state was loaded from a segment file),
+//! and `zkm_b200_init(0, ..)` once per process.
 //!
 //! What stays on the host and why the order below reproduces the reference's files byte for byte:
 //!  * `rtrace` (the segment's memory image) also holds hash pages: every first touch of a page records the L1 / L2 / root hash
@@ -56,6 +57,7 @@ extern "C" {
         image_id_out: *mut u8, page_hash_root_out: *mut u8, err: *mut *mut c_char,
     ) -> c_int;
     fn zkm_b200_pagetree_page(t: *const c_void, page_index: u32, out: *mut u8, present: *mut c_int, err: *mut *mut c_char) -> c_int;
+    fn zkm_b200_pagetree_set_page(t: *mut c_void, page_index: u32, data: *const u8, err: *mut *mut c_char) -> c_int;
     fn zkm_b200_free_string(s: *mut c_char);
 }
 
@@ -71,6 +73,16 @@ pub fn splitter_create() -> *mut c_void {
     let (mut s, mut err) = (core::ptr::null_mut(), core::ptr::null_mut());
     check(unsafe { zkm_b200_splitter_create(&mut s, &mut err) }, err);
     s
+}
+
+/// A state resumed from a segment file (`State::load_seg`, as `split_seg_into_segs` does, utils.rs:62-109) has its hash pages in
+/// memory already: hand them to the library's tree before the first split.  Not needed for `split_prog_into_segs`.
+pub fn splitter_seed(s: *mut c_void, memory: &crate::memory::Memory) {
+    let tree = unsafe { zkm_b200_splitter_pagetree(s) };
+    for (index, page) in memory.pages.range(0x80000u32..=0x81020u32) {
+        let mut err = core::ptr::null_mut();
+        check(unsafe { zkm_b200_pagetree_set_page(tree, *index, page.borrow().data.as_ptr(), &mut err) }, err);
+    }
 }
 
 pub fn splitter_destroy(s: *mut c_void) {

@@ -106,6 +106,26 @@ def test_oracle_page_hashing_matches_the_reference_walk(orc):
     tree.close()
 
 
+def test_page_tree_is_seeded_without_a_device():
+    """zkm_b200_pagetree_set_page / _page are host-side bookkeeping (a resumed emulator state brings its hash pages along): they
+    work before zkm_b200_init, refuse main-memory indices, and a page that was never set or hashed reads as absent."""
+    from zkm_b200 import lib as zl
+    lib = zl.load()
+    tree = zl.PageTree(lib)
+    rng = np.random.default_rng(2)
+    pages = {hp: rng.integers(0, 256, size=4096, dtype=np.uint8) for hp in (0x80000, 0x80FFF, 0x81000, 0x8101F, 0x81020)}
+    for hp, data in pages.items():
+        tree.set_page(hp, data.tobytes())
+    for hp, data in pages.items():
+        assert (tree.page(hp) == data).all()
+    tree.set_page(0x81020, bytes(4096))                                  # overwriting is allowed
+    assert not tree.page(0x81020).any() and tree.page(0x80001) is None
+    for bad in (0, 0x7FFFF, 0x81021, 0xFFFFF):
+        with pytest.raises(zl.ZkmError, match="not a hash page index"):
+            tree.set_page(bad, bytes(4096))
+    tree.close()
+
+
 @pytest.mark.gpu
 def test_device_page_hashing_matches_oracle(zkm, orc):
     from zkm_b200 import lib as zl

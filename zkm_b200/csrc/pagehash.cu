@@ -173,6 +173,18 @@ int zkm_b200_pagetree_page(const zkm_pagetree_t* t, uint32_t page_index, uint8_t
     ZKM_API_END
 }
 
+// A state resumed from a segment file (State::load_seg, emulator/src/state.rs:141-190; split_seg_into_segs, utils.rs:62-109) brings
+// its hash pages in the memory image: they seed the tree before the first split.  Host-only.
+int zkm_b200_pagetree_set_page(zkm_pagetree_t* t, uint32_t page_index, const uint8_t* data, char** err) {
+    ZKM_API_BEGIN
+    ZKM_CHECK(t && data, "null argument");
+    ZKM_CHECK(page_index >= (zkm::PT_MAX_MEMORY >> 12) && page_index <= zkm::PT_ROOT_PAGE, "not a hash page index");
+    zkm::PageTreeDev::Page p;
+    memcpy(p.data(), data, zkm::PAGE_BYTES);
+    t->t.hash_pages[page_index] = p;
+    ZKM_API_END
+}
+
 // ---- the whole split_segment (emulator/src/state.rs:1477-1530) but the step loop: hashing on the device, the pre_* bookkeeping of
 // InstrumentedState (:556-596) and the segment file.
 struct zkm_splitter {

@@ -37,7 +37,7 @@ EXPORTS = [
     "zkm_b200_worker_create", "zkm_b200_worker_bind", "zkm_b200_worker_destroy",
     "zkm_b200_shard_unique_id", "zkm_b200_shard_init", "zkm_b200_shard_shutdown",
     "zkm_b200_prove_with_traces", "zkm_b200_prove_with_trace_rows", "zkm_b200_memory_trace", "zkm_b200_prove_with_memory_ops", "zkm_b200_prove_with_ops", "zkm_b200_table_from_ops", "zkm_b200_prove_system", "zkm_b200_prove_system_device", "zkm_b200_synth_columns_device", "zkm_b200_synth_trace_device", "zkm_b200_synth_trace", "zkm_b200_system_shape", "zkm_b200_timer_start", "zkm_b200_timer_stop", "zkm_b200_profile_enable", "zkm_b200_profile_reset", "zkm_b200_profile_get", "zkm_b200_profile_get_traffic", "zkm_b200_timing_enable", "zkm_b200_last_timing", "zkm_b200_layout_check", "zkm_b200_layout_describe", "zkm_b200_proof_table_json", "zkm_b200_public_values_json", "zkm_b200_profile_families",
-    "zkm_b200_stage_table", "zkm_b200_segment_json", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page",
+    "zkm_b200_stage_table", "zkm_b200_segment_json", "zkm_b200_hash_pages", "zkm_b200_pagetree_create", "zkm_b200_pagetree_destroy", "zkm_b200_pagetree_split", "zkm_b200_pagetree_page", "zkm_b200_pagetree_set_page",
     "zkm_b200_splitter_create", "zkm_b200_splitter_destroy", "zkm_b200_splitter_pagetree", "zkm_b200_splitter_segment_count", "zkm_b200_splitter_split",
 ]
 
@@ -420,7 +420,15 @@ class PageTree:
         lib.zkm_b200_pagetree_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                                 C.POINTER(C.c_void_p)]
         lib.zkm_b200_pagetree_page.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        lib.zkm_b200_pagetree_set_page.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]
         check(lib, lib.zkm_b200_pagetree_create(C.byref(self.h), C.byref(err)), err)
+
+    def set_page(self, index: int, data):
+        """Seeds one hash page (a state resumed from a segment file carries them in its memory image)."""
+        pg = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        assert pg.size == 4096
+        err = C.c_void_p()
+        check(self.lib, self.lib.zkm_b200_pagetree_set_page(self.h, index, pg.ctypes.data, C.byref(err)), err)
 
     def split(self, indices, pages, registers: bytes, pc: int):
         idx = np.ascontiguousarray(indices, dtype=np.uint32)

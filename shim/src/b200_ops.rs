@@ -4,7 +4,8 @@
 //! `prove_with_outputs` -> `generate_traces` -> `prove_with_traces` (prover.rs:58-128).
 //!
 //! SOURCE ONLY (no cargo in this image), written against zkMIPS/zkm @ 04117ce3.  Needs, besides `b200.rs`:
-//!  * `pub(crate)` on the three private fields of `logic::Operation` (logic.rs:100-107: operator, input0, input1);
+//!  * `pub(crate)` on the three private fields of `logic::Operation` (logic.rs:100-107: operator, input0, input1) -- part of
+//!    `shim/prover_b200.patch`;
 //!  * `generate_traces` to hand back the `Traces` instead of calling `into_tables` (generation/mod.rs:169-186).
 //! The log formats are the ones documented next to `zkm_op_log_t`; `tests/test_gpu_tracegen.py` checks each of them against the
 //! restated reference generators and the all-logs proof against the proof over host-built tables.

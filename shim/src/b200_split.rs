@@ -3,10 +3,11 @@
 //! SOURCE ONLY (no cargo in this image), written against zkMIPS/zkm @ 04117ce3.  Replaces the body of `split_segment`
 //! (emulator/src/state.rs:1477-1530): `Memory::update_page_hash` + `compute_image_id` (memory.rs:415-471, 129 Poseidon
 //! permutations per dirty 4 KiB page, on one core) and `serde_json::to_vec(&segment)` become one call of
-//! `zkm_b200_splitter_split` (include/zkm_b200.h).  Needs `pub(crate)` on `Memory::{pages, rtrace, wtrace}` (memory.rs:121-136) and
-//! on the `pre_*` fields of `InstrumentedState` (state.rs:552-560), one `splitter: *mut c_void` field created in
-//! `InstrumentedState::new` with `splitter_create` (followed by `splitter_seed` when the state was loaded from a segment file),
-//! and `zkm_b200_init(0, ..)` once per process.
+//! `zkm_b200_splitter_split` (include/zkm_b200.h).  `shim/emulator_b200.patch` makes the rest of the crate ready for it: `pub(crate)`
+//! on `Memory::{pages, rtrace, wtrace}` (memory.rs:121-136) and on the `pre_*` fields of `InstrumentedState` (state.rs:552-560), a
+//! `splitter: *mut c_void` field created in `InstrumentedState::new` with `splitter_create`, and `split_segment` forwarding here
+//! under the `b200` feature.  A state loaded from a segment file calls `splitter_seed` before its first split; the host binary
+//! calls `zkm_b200_init(0, ..)` once per process.
 //!
 //! What stays on the host and why the order below reproduces the reference's files byte for byte:
 //!  * `rtrace` (the segment's memory image) also holds hash pages: every first touch of a page records the L1 / L2 / root hash

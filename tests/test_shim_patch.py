@@ -1,0 +1,128 @@
+"""shim/*.patch are real unified diffs: applied with patch(1) to a scratch copy of the reference checkout they must go in without
+fuzz or rejects and leave the edits the Rust sources in shim/src/ rely on.  Also: the committed patches are what
+tools/gen_shim_patch.py generates.  Needs /root/reference (present where the CPU suite runs; skipped elsewhere); cargo is not
+available, so compiling the result remains the maintainer's step."""
+import pathlib
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+REF = pathlib.Path("/root/reference")
+
+pytestmark = pytest.mark.skipif(not (REF / "prover/src/prover.rs").exists(), reason="reference checkout not present")
+
+
+def test_patches_apply_to_the_reference(tmp_path):
+    for sub in ("prover", "emulator"):
+        (tmp_path / sub).mkdir()
+        shutil.copy(REF / sub / "Cargo.toml", tmp_path / sub / "Cargo.toml")
+        shutil.copytree(REF / sub / "src", tmp_path / sub / "src")
+    for name in ("prover_b200.patch", "emulator_b200.patch"):
+        r = subprocess.run(["patch", "-p1", "--no-backup-if-mismatch", "-i", str(ROOT / "shim" / name)], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "fuzz" not in r.stdout and "offset" not in r.stdout and not list(tmp_path.rglob("*.rej")), r.stdout
+    for src, dst in (("b200.rs", "prover/src"), ("b200_ops.rs", "prover/src"), ("b200_split.rs", "emulator/src")):
+        shutil.copy(ROOT / "shim/src" / src, tmp_path / dst / src)
+    prover = (tmp_path / "prover/src/prover.rs").read_text()
+    assert prover.count('#[cfg(feature = "b200")]\npub(crate) fn prove_with_traces<') == 1
+    assert prover.count('#[cfg(not(feature = "b200"))]\npub(crate) fn prove_with_traces<') == 1
+    assert "crate::b200::prove_with_traces_generic::<F, C, D>(config, trace_poly_values, public_values)?" in prover
+    assert prover.count("C: GenericConfig<D, F = F> + 'static,") == 6          # five entry points + the twin
+    lib = (tmp_path / "prover/src/lib.rs").read_text()
+    assert '#[cfg(feature = "b200")]\npub mod b200;' in lib and '#[cfg(feature = "b200")]\npub mod b200_ops;' in lib
+    assert "b200 = []" in (tmp_path / "prover/Cargo.toml").read_text() and "b200 = []" in (tmp_path / "emulator/Cargo.toml").read_text()
+    # what the shim sources reach into exists with the visibility they need
+    logic = (tmp_path / "prover/src/logic.rs").read_text()
+    for f in ("operator: Op", "input0: u32", "input1: u32"):
+        assert f"pub(crate) {f}," in logic
+    memory, state = (tmp_path / "emulator/src/memory.rs").read_text(), (tmp_path / "emulator/src/state.rs").read_text()
+    for f in ("pages:", "rtrace:", "wtrace:"):
+        assert f"pub(crate) {f}" in memory
+    split = (ROOT / "shim/src/b200_split.rs").read_text()
+    for f in ("pre_pc", "pre_image_id", "pre_hash_root", "pre_input", "pre_input_ptr", "pre_public_values", "pre_public_values_ptr", "splitter"):
+        assert f"pub(crate) {f}:" in state and f"self.{f}" in split, f
+    assert "splitter: crate::b200_split::splitter_create()," in state and "self.split_segment_b200(proof, output, new_writer)" in state
+    assert state.count("pub fn split_segment<W: Write>(") == 2 and '#[cfg(not(feature = "b200"))]\n    pub fn split_segment<W: Write>(' in state
+    # every `use crate::...` of the shim sources names a module / item that exists in the patched tree
+    for src, crate_dir in (("b200.rs", "prover/src"), ("b200_ops.rs", "prover/src"), ("b200_split.rs", "emulator/src")):
+        import re
+        text = (ROOT / "shim/src" / src).read_text()
+        for mod in set(re.findall(r"use crate::(\w+)", text)) | set(re.findall(r"\bcrate::(\w+)::", text)):
+            d = tmp_path / crate_dir
+            assert (d / f"{mod}.rs").exists() or (d / mod / "mod.rs").exists(), f"{src}: crate::{mod}"
+
+
+def test_committed_patches_are_the_generated_ones():
+    sys.path.insert(0, str(ROOT / "tools"))
+    import gen_shim_patch
+    prover, emulator = gen_shim_patch.generate(REF)
+    assert prover == (ROOT / "shim/prover_b200.patch").read_text()
+    assert emulator == (ROOT / "shim/emulator_b200.patch").read_text()
+
+
+def _crate_uses(text):
+    """`use crate::a::b::{X, Y as Z};` / `use crate::a::X;` -> [(['a', 'b'], 'X'), ...]"""
+    import re
+    out = []
+    for path, group, single in re.findall(r"use crate::((?:\w+::)*)(?:\{([^}]*)\}|(\w+)(?:\s+as\s+\w+)?)\s*;", text):
+        mods = [m for m in path.split("::") if m]
+        names = [n.split(" as ")[0].strip() for n in group.split(",")] if group else [single]
+        out += [(mods, n) for n in names if n and n != "self"]
+    return out
+
+
+def test_shim_imports_resolve_in_the_reference():
+    """Poor man's name resolution (no rustc here): every item the shim sources import from the host crate is defined, or re-exported,
+    in the module file the path names, and is not private."""
+    import re
+    checked = 0
+    for src, crate_dir in (("b200.rs", "prover/src"), ("b200_ops.rs", "prover/src"), ("b200_split.rs", "emulator/src")):
+        text = (ROOT / "shim/src" / src).read_text()
+        for mods, name in _crate_uses(text):
+            if mods and mods[0] in ("b200", "b200_ops", "b200_split"):
+                target = (ROOT / "shim/src" / f"{mods[0]}.rs").read_text()
+            else:
+                base = REF / crate_dir
+                # the last path element may itself be the item's module (use crate::logic;)
+                cands = [base.joinpath(*mods).with_suffix(".rs"), base.joinpath(*mods) / "mod.rs"] if mods else []
+                cands += [base / f"{name}.rs", base / name / "mod.rs"] if not mods else []
+                files = [c for c in cands if c.exists()]
+                assert files, f"{src}: no module file for crate::{'::'.join(mods + [name])}"
+                if not mods:
+                    checked += 1
+                    continue                                  # a module import: the file exists
+                target = files[0].read_text()
+            pat = rf"^\s*pub(?:\(crate\))?\s+(?:unsafe\s+)?(?:const\s+fn|fn|struct|enum|trait|type|const|static|union)\s+{name}\b|^\s*pub(?:\(crate\))?\s+use\s+[^;]*\b{name}\b"
+            assert re.search(pat, target, flags=re.M), f"{src}: crate::{'::'.join(mods)}::{name} is not a visible item of its module"
+            checked += 1
+    assert checked >= 25
+
+
+def test_shim_reads_fields_the_reference_structs_have():
+    """b200_ops.rs walks `Traces` and its operation records field by field: each field it names exists upstream."""
+    import re
+    ops = re.sub(r"//[^\n]*", "", (ROOT / "shim/src/b200_ops.rs").read_text())
+    traces_rs = (REF / "prover/src/witness/traces.rs").read_text()
+    fields = set(re.findall(r"\btraces\.(\w+)", ops))
+    assert {"arithmetic_ops", "logic_ops", "memory_ops", "cpu", "poseidon_inputs", "keccak_inputs", "keccak_sponge_ops", "poseidon_sponge_ops",
+            "sha_extend_inputs", "sha_extend_sponge_ops", "sha_compress_inputs", "sha_compress_sponge_ops"} <= fields
+    for f in fields:
+        assert re.search(rf"^\s*pub(?:\(crate\))?\s+{f}\s*:", traces_rs, flags=re.M), f"Traces has no field {f}"
+    defs = {"MemoryOp": "prover/src/witness/memory.rs", "MemoryAddress": "prover/src/witness/memory.rs",
+            "KeccakSpongeOp": "prover/src/keccak_sponge/keccak_sponge_stark.rs", "PoseidonSpongeOp": "prover/src/poseidon_sponge/poseidon_sponge_stark.rs",
+            "ShaExtendSpongeOp": "prover/src/sha_extend_sponge/sha_extend_sponge_stark.rs",
+            "ShaCompressSpongeOp": "prover/src/sha_compress_sponge/sha_compress_sponge_stark.rs"}
+    used = {"MemoryOp": ["address", "timestamp", "kind", "value", "filter"], "MemoryAddress": ["context", "segment", "virt"],
+            "KeccakSpongeOp": ["base_address", "timestamp", "input"], "PoseidonSpongeOp": ["base_address", "timestamp", "input"],
+            "ShaExtendSpongeOp": ["base_address", "timestamp", "input", "i", "output_address"],
+            "ShaCompressSpongeOp": ["base_address", "timestamp", "input", "w_i_s"]}
+    for struct, path in defs.items():
+        text = (REF / path).read_text()
+        m = re.search(rf"pub(?:\(crate\))?\s+struct\s+{struct}\s*\{{(.*?)\n\}}", text, flags=re.S)
+        assert m, struct
+        for f in used[struct]:
+            assert re.search(rf"\bpub(?:\(crate\))?\s+{f}\s*:", m.group(1)), f"{struct}.{f}"
+            assert re.search(rf"\.{f}\b", ops), f"b200_ops.rs no longer reads .{f}"

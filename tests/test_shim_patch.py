@@ -126,3 +126,48 @@ def test_shim_reads_fields_the_reference_structs_have():
         for f in used[struct]:
             assert re.search(rf"\bpub(?:\(crate\))?\s+{f}\s*:", m.group(1)), f"{struct}.{f}"
             assert re.search(rf"\.{f}\b", ops), f"b200_ops.rs no longer reads .{f}"
+
+
+def _literal_fields(text, name):
+    """Field names of every struct literal `name { ... }` in `text` (brace matching, top-level commas)."""
+    import re
+    out = []
+    for m in re.finditer(rf"\b{name}\s*\{{", text):
+        depth, i, start = 1, m.end(), m.end()
+        while depth:
+            depth += {"{": 1, "}": -1}.get(text[i], 0)
+            i += 1
+        body, fields, level, cur = text[start:i - 1], [], 0, ""
+        for ch in body:
+            if ch in "{([":
+                level += 1
+            elif ch in "})]":
+                level -= 1
+            if ch == "," and level == 0:
+                fields.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        fields.append(cur)
+        out.append(sorted(re.match(r"\s*(\w+)", f).group(1) for f in fields if f.strip()))
+    return out
+
+
+def test_shim_struct_literals_name_exactly_the_upstream_fields():
+    """A struct literal must list every field: the typed proof structs decode_all_proof builds are compared with their definitions
+    in the reference (proof.rs, cross_table_lookup.rs).  The plonky2 structs (FriProof, ...) are not in the tree and stay unchecked."""
+    import re
+    shim = re.sub(r"//[^\n]*", "", (ROOT / "shim/src/b200.rs").read_text())
+    where = {"AllProof": "proof.rs", "StarkProofWithMetadata": "proof.rs", "StarkProof": "proof.rs", "StarkOpeningSet": "proof.rs",
+             "PublicValues": "proof.rs", "MemRoots": "proof.rs", "GrandProductChallenge": "cross_table_lookup.rs",
+             "GrandProductChallengeSet": "cross_table_lookup.rs"}
+    for name, path in where.items():
+        text = (REF / "prover/src" / path).read_text()
+        m = re.search(rf"pub(?:\(crate\))?\s+struct\s+{name}\b[^{{;]*\{{(.*?)\n\}}", text, flags=re.S)
+        assert m, name
+        want = sorted(re.findall(r"^\s*pub(?:\(crate\))?\s+(\w+)\s*:", m.group(1), flags=re.M))
+        assert want, name
+        lits = [f for f in _literal_fields(shim, name)]
+        assert lits, f"b200.rs builds no {name}"
+        for got in lits:
+            assert got == want, f"{name}: shim {got} != reference {want}"

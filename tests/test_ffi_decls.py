@@ -132,3 +132,29 @@ def test_rust_repr_c_structs_match_the_header():
             assert got == want, f"{src}: {name}\n rust {got}\n C    {want}"
             checked.add(name)
     assert {"ZkmTable", "ZkmStarkConfig", "ZkmTableRows", "ZkmOpLog", "ZkmSplitState"} <= checked, checked
+
+
+def test_rust_layout_keys_match_the_header_and_are_all_reported():
+    """The layout handshake is keyed by numbers: the `lk::*` constants of shim/src/b200.rs must be the ZKM_LK_* values of the header
+    (and of the reference-derived fixture), and layout_pairs() must report every CPU key exactly once -- a key left out would
+    simply not be checked."""
+    import json
+    enum = re.search(r"enum\s*\w*\s*\{([^}]*ZKM_LK_NUM_COLUMNS[^}]*)\}", _strip_comments((ROOT / "include/zkm_b200.h").read_text())).group(1)
+    header, nxt = {}, 0
+    for item in enum.split(","):
+        m = re.match(r"\s*ZKM_LK_(\w+)\s*(?:=\s*(\d+))?\s*$", item)
+        if not m:
+            assert not item.strip(), item
+            continue
+        nxt = int(m.group(2)) if m.group(2) else nxt
+        header[m.group(1)] = nxt
+        nxt += 1
+    shim = _strip_comments((ROOT / "shim/src/b200.rs").read_text())
+    lk = dict((k, int(v)) for k, v in re.findall(r"pub const (\w+): u32 = (\d+);", re.search(r"mod lk \{(.*?)\n\}", shim, flags=re.S).group(1)))
+    assert lk == header and len(lk) >= 50
+    fixture = json.loads((ROOT / "tests/golden/column_layout_v1.json").read_text())["keys"]
+    assert {k[len("ZKM_LK_"):]: v for k, v in fixture.items()} == {k: v for k, v in header.items() if k != "NUM_COLUMNS"}
+    body = re.search(r"pub fn layout_pairs.*?\n\}", shim, flags=re.S).group(0)
+    used = re.findall(r"\(lk::(\w+)", body)
+    assert sorted(used) == sorted(set(used)), "a key is reported twice"
+    assert set(used) | {"NUM_COLUMNS"} == set(lk) | {"NUM_COLUMNS"} and "NUM_COLUMNS" in re.findall(r"lk::(\w+)", body)

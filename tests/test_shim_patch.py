@@ -171,3 +171,21 @@ def test_shim_struct_literals_name_exactly_the_upstream_fields():
         assert lits, f"b200.rs builds no {name}"
         for got in lits:
             assert got == want, f"{name}: shim {got} != reference {want}"
+
+
+def test_layout_pairs_reads_fields_that_exist_upstream():
+    """Every field or view accessor layout_pairs() of shim/src/b200.rs touches is declared in the reference's column structs
+    (the files the layout fixture was derived from)."""
+    import json
+    import re
+    shim = re.sub(r"//[^\n]*", "", (ROOT / "shim/src/b200.rs").read_text())
+    body = re.search(r"pub fn layout_pairs.*?\n\}", shim, flags=re.S).group(0)
+    files = json.loads((ROOT / "tests/golden/column_layout_v1.json").read_text())["reference_files"]
+    decls = "\n".join((REF / f).read_text() for f in files)
+    rust_methods = {"iter", "min", "unwrap", "enumerate", "push", "extend_from_slice", "into_iter", "flat_map", "collect"}
+    names = set(re.findall(r"\.(\w+)", body)) - rust_methods
+    assert len(names) >= 55
+    for n in sorted(names):
+        field = re.search(rf"^\s*pub(?:\(crate\))?\s+{n}\s*:", decls, flags=re.M)
+        accessor = re.search(rf"\bfn\s+{n}\s*\(\s*&self", decls)
+        assert field or accessor, f"layout_pairs reads .{n}, which the reference's column structs do not declare"

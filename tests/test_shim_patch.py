@@ -189,3 +189,32 @@ def test_layout_pairs_reads_fields_that_exist_upstream():
         field = re.search(rf"^\s*pub(?:\(crate\))?\s+{n}\s*:", decls, flags=re.M)
         accessor = re.search(rf"\bfn\s+{n}\s*\(\s*&self", decls)
         assert field or accessor, f"layout_pairs reads .{n}, which the reference's column structs do not declare"
+
+
+def test_fingerprint_test_source_names_upstream_items():
+    """shim/fingerprint_test.rs (the cargo test of INTEGRATION.md section 3) is appended to cross_table_lookup.rs upstream: the struct
+    fields and functions it uses are declared there / in the modules it imports."""
+    import re
+    src = re.sub(r"//[^\n]*", "", (ROOT / "shim/fingerprint_test.rs").read_text())
+    P = REF / "prover/src"
+
+    def fields(path, struct):
+        m = re.search(rf"struct\s+{struct}\b[^{{;]*\{{(.*?)\n\}}", (P / path).read_text(), flags=re.S)
+        assert m, struct
+        return set(re.findall(r"^\s*(?:pub(?:\([a-z]+\))?\s+)?(\w+)\s*:", m.group(1), flags=re.M))
+
+    assert set(re.findall(r"\bs\.(\w+)", src)) == fields("all_stark.rs", "AllStark") - {"cross_table_lookups"}
+    assert set(re.findall(r"\bl\.(\w+)", src)) == fields("lookup.rs", "Lookup")
+    assert set(re.findall(r"\bt\.(\w+)", src)) - {"iter"} == fields("cross_table_lookup.rs", "TableWithColumns")
+    assert set(re.findall(r"\bctl\.(\w+)", src)) == fields("cross_table_lookup.rs", "CrossTableLookup")
+    ctl_rs, cc_rs, all_rs = (P / "cross_table_lookup.rs").read_text(), (P / "constraint_consumer.rs").read_text(), (P / "all_stark.rs").read_text()
+    assert re.search(r"pub fn eval_with_next<FE, P, const D: usize>\(&self, v: &\[P\], next_v: &\[P\]\) -> P", ctl_rs)
+    assert re.search(r"pub\(crate\) fn eval_filter<FE, P, const D: usize>\(&self, v: &\[P\], next_v: &\[P\]\) -> P", ctl_rs)
+    new = re.search(r"pub fn new\(\s*alphas: Vec<P::Scalar>,\s*z_last: P,\s*lagrange_basis_first: P,\s*lagrange_basis_last: P,\s*\) -> Self", cc_rs)
+    assert new and "pub fn accumulators(self) -> Vec<P>" in cc_rs
+    assert len(re.search(r"ConstraintConsumer::<F>::new\((.*?)\);", src, flags=re.S).group(1).split("F::from_canonical_u64(")) - 1 == 5   # 2 alphas + 3
+    assert "pub(crate) fn all_cross_table_lookups<F: Field>() -> Vec<CrossTableLookup<F>>" in all_rs and "pub(crate) fn all() -> [Self; NUM_TABLES]" in all_rs
+    # the column counts it hard-codes are the reference's (and bench.py's)
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert [int(x) for x in re.search(r"ncols: \[usize; 12\] = \[([^\]]*)\]", src).group(1).split(",")] == bench.NCOLS

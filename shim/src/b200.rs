@@ -228,14 +228,22 @@ impl<'a> Reader<'a> {
         Ok(v)
     }
     fn words(&mut self, n: usize) -> Result<&'a [u64]> {
-        let s = self.buf.get(self.pos..self.pos + n).ok_or_else(|| anyhow!("proof buffer truncated"))?;
-        self.pos += n;
+        // lengths come from the buffer: neither pos + n nor n * unit may be trusted not to wrap
+        let end = self.pos.checked_add(n).filter(|&e| e <= self.buf.len()).ok_or_else(|| anyhow!("proof buffer truncated"))?;
+        let s = &self.buf[self.pos..end];
+        self.pos = end;
         Ok(s)
     }
     /// "vec X": a length word, then `unit` words per item.
     fn vec(&mut self, unit: usize) -> Result<&'a [u64]> {
         let n = self.u()? as usize;
-        self.words(n * unit)
+        self.words(n.checked_mul(unit).ok_or_else(|| anyhow!("proof buffer truncated"))?)
+    }
+    /// A number of items that take at least one word each: bounded by what is left of the buffer, hence safe as a capacity.
+    fn count(&mut self) -> Result<usize> {
+        let n = self.u()? as usize;
+        ensure!(n <= self.buf.len() - self.pos, "proof buffer truncated");
+        Ok(n)
     }
 }
 
@@ -272,21 +280,21 @@ fn decode_stark_proof(r: &mut Reader) -> Result<StarkProofWithMetadata<F, C, D>>
         ctl_zs_first: fs(r.vec(1)?),
         quotient_polys: exts(r.vec(2)?),
     };
-    let ncaps = r.u()? as usize;
+    let ncaps = r.count()?;
     let mut commit_phase_merkle_caps = Vec::with_capacity(ncaps);
     for _ in 0..ncaps {
         commit_phase_merkle_caps.push(cap(r.vec(4)?));
     }
-    let nq = r.u()? as usize;
+    let nq = r.count()?;
     let mut query_round_proofs = Vec::with_capacity(nq);
     for _ in 0..nq {
-        let noracles = r.u()? as usize;
+        let noracles = r.count()?;
         let mut evals_proofs = Vec::with_capacity(noracles);
         for _ in 0..noracles {
             let leaf = fs(r.vec(1)?);
             evals_proofs.push((leaf, path(r.vec(4)?)));
         }
-        let nsteps = r.u()? as usize;
+        let nsteps = r.count()?;
         let mut steps = Vec::with_capacity(nsteps);
         for _ in 0..nsteps {
             let evals = exts(r.vec(2)?);
@@ -314,7 +322,7 @@ pub fn decode_all_proof(buf: &[u64]) -> Result<AllProof<F, C, D>> {
     ensure!(r.u()? == PROOF_MAGIC, "bad proof magic");
     ensure!(r.u()? == 1, "bad proof version");
     ensure!(r.u()? as usize == NUM_TABLES, "proof is not an AllStark proof");
-    let nch = r.u()? as usize;
+    let nch = r.count()?;
     let mut challenges = Vec::with_capacity(nch);
     for _ in 0..nch {
         let beta = f(r.u()?);

@@ -158,3 +158,31 @@ def test_rust_layout_keys_match_the_header_and_are_all_reported():
     used = re.findall(r"\(lk::(\w+)", body)
     assert sorted(used) == sorted(set(used)), "a key is reported twice"
     assert set(used) | {"NUM_COLUMNS"} == set(lk) | {"NUM_COLUMNS"} and "NUM_COLUMNS" in re.findall(r"lk::(\w+)", body)
+
+
+def test_three_decoders_read_the_buffer_in_the_same_order():
+    """The flat proof buffer has three readers: the Python walk of tests/test_wire_format.py (run against real proofs), the C++
+    decoder of include/zkm_b200.hpp (compiled, round-trip tested) and the Rust decoder of shim/src/b200.rs (never compiled here).
+    Their per-table read sequences -- written in source order = execution order in all three -- must be the same list of
+    (12 fixed words | vec of unit k | count), and each must assign the reads to the same field names."""
+    rust = _strip_comments((ROOT / "shim/src/b200.rs").read_text())
+    rust = re.search(r"fn decode_stark_proof.*?\n\}", rust, flags=re.S).group(0)
+    r_seq = [("w12" if a.startswith("words") else "n" if a in ("u()", "count()") else "v" + a[4]) for a in
+             re.findall(r"r\.(words\(12\)|vec\(\d\)|count\(\)|u\(\))", rust)]
+    py = (ROOT / "tests/test_wire_format.py").read_text()
+    py = py[py.index("for _ in range(nt):"):py.index("out.append(d)")]
+    p_seq = [("w12" if a.startswith("words") else "n" if a == "u()" else "v" + a[4]) for a in re.findall(r"r\.(words\(12\)|vec\(\d\)|u\(\))", py)]
+    cpp = _strip_comments((ROOT / "include/zkm_b200.hpp").read_text())
+    cpp = re.search(r"inline StarkProofWithMetadata decode_table\(Reader& r\) \{.*?\n\}", cpp, flags=re.S).group(0)
+    unit = {"hashes()": "v4", "exts()": "v2", "fs()": "v1", "u()": "n"}
+    c_seq = [("w12" if a.startswith("words") else unit[a]) for a in re.findall(r"r\.(words\(12\)|hashes\(\)|exts\(\)|fs\(\)|u\(\))", cpp)]
+    want = ["w12", "v4", "v4", "v4", "v2", "v2", "v2", "v2", "v1", "v2", "n", "v4", "n", "n", "v1", "v4", "n", "v2", "v4", "v2", "n"]
+    assert r_seq == want and p_seq == want and c_seq == want, (r_seq, p_seq, c_seq)
+    # field order inside the openings (all six are vectors of the same shape but for ctl_zs_first: a swap would not change the sequence)
+    order = ["local_values", "next_values", "auxiliary_polys", "auxiliary_polys_next", "ctl_zs_first", "quotient_polys"]
+    assert re.findall(r"(\w+): (?:exts|fs)\(r\.vec", rust) == order
+    assert re.findall(r'"(\w+)": r\.vec', py[py.index('d["openings"]'):py.index("ncaps = r.u()")]) == order
+    assert re.findall(r"p\.openings\.(\w+) = r\.", cpp) == order
+    caps = ["trace_cap", "auxiliary_polys_cap", "quotient_polys_cap"]
+    assert re.findall(r"let (\w+) = cap\(r\.vec\(4\)", rust) == caps and re.findall(r"p\.(\w+) = r\.hashes\(\)", cpp) == caps
+    assert re.findall(r'"(\w+)": H\(r\.vec\(4\)\)', py)[:3] == caps

@@ -46,7 +46,8 @@ def expected_tables(proof):
         d = {"trace_cap": H(r.vec(4)), "auxiliary_polys_cap": H(r.vec(4)), "quotient_polys_cap": H(r.vec(4))}
         d["openings"] = {"local_values": r.vec(2), "next_values": r.vec(2), "auxiliary_polys": r.vec(2),
                          "auxiliary_polys_next": r.vec(2), "ctl_zs_first": r.vec(1), "quotient_polys": r.vec(2)}
-        caps = [H(r.vec(4)) for _ in range(r.u())]
+        ncaps = r.u()
+        caps = [H(r.vec(4)) for _ in range(ncaps)]
         rounds = []
         for _ in range(r.u()):
             ev = []

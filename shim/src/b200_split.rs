@@ -86,6 +86,8 @@ pub fn splitter_seed(s: *mut c_void, memory: &crate::memory::Memory) {
     }
 }
 
+/// `InstrumentedState` cannot implement `Drop` (split_prog_into_segs moves `state` out of it, utils.rs:51-55): call this where the
+/// state is given up, or leave the one splitter of a run to process exit.
 pub fn splitter_destroy(s: *mut c_void) {
     unsafe { zkm_b200_splitter_destroy(s) }
 }

@@ -32,7 +32,7 @@ use plonky2::hash::merkle_tree::MerkleCap;
 use plonky2::hash::poseidon::{PoseidonHash, PoseidonPermutation};
 use plonky2::hash::hashing::PlonkyPermutation;
 use plonky2::plonk::config::{GenericConfig, PoseidonGoldilocksConfig};
-use plonky2::util::log2_strict;
+use plonky2_util::log2_strict; // as prover.rs:19 imports it
 
 use crate::all_stark::NUM_TABLES;
 use crate::config::StarkConfig;

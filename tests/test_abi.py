@@ -108,3 +108,53 @@ def test_column_layout_handshake_against_reference_derived_fixture():
     unknown = (C.c_uint32 * 2)(9999, 1)
     assert lib.zkm_b200_layout_check(unknown, 1, C.byref(err)) == -1
     lib.zkm_b200_free_string(err)
+
+
+def test_header_is_plain_c_and_cxx():
+    """include/zkm_b200.h is the boundary a cgo / Rust-bindgen / C caller binds: it must compile on its own as C99 and as C++11
+    (pedantic, warnings as errors), and a C program using the host-only entry points links against the library."""
+    import subprocess
+    hdr = str(ROOT / "include/zkm_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+
+
+def test_c_program_links_and_uses_the_host_only_entry_points(tmp_path):
+    import subprocess
+    lib_path = _built()
+    src = tmp_path / "c_user.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "zkm_b200.h"
+int main(void) {
+    zkm_stark_config_t cfg;
+    zkm_b200_standard_fast_config(&cfg);
+    printf("config %u %u %u %u\n", cfg.rate_bits, cfg.cap_height, cfg.pow_bits, cfg.num_queries);
+    char* err = NULL;
+    zkm_pagetree_t* t = NULL;
+    if (zkm_b200_pagetree_create(&t, &err)) return 1;
+    unsigned char page[4096], back[4096];
+    memset(page, 0x5A, sizeof page);
+    if (zkm_b200_pagetree_set_page(t, 0x81020u, page, &err)) return 2;
+    int present = 0;
+    if (zkm_b200_pagetree_page(t, 0x81020u, back, &present, &err) || !present || memcmp(page, back, sizeof page)) return 3;
+    if (zkm_b200_pagetree_set_page(t, 5u, page, &err) == 0) return 4;
+    printf("error: %s\n", err);
+    zkm_b200_free_string(err);
+    zkm_b200_pagetree_destroy(t);
+    uint64_t junk[4] = {1, 2, 3, 4};
+    char* json = NULL; size_t len = 0;
+    if (zkm_b200_public_values_json(junk, 4, &json, &len, &err) == 0) return 5;
+    printf("error: %s\n", err);
+    zkm_b200_free_string(err);
+    return 0;
+}
+''')
+    exe = tmp_path / "c_user"
+    cuda = "/usr/local/cuda/lib64"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-L", str(lib_path.parent), "-lzkm_b200",
+                    f"-Wl,-rpath,{lib_path.parent}", f"-Wl,-rpath,{cuda}", f"-Wl,-rpath-link,{cuda}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.splitlines() == ["config 2 4 16 37", "error: not a hash page index", "error: bad proof magic"]
